@@ -1,0 +1,85 @@
+/* tenscalc_b200 -- C ABI of the batched, Blackwell-native interior-point backend.
+ *
+ * This header is the drop-in boundary.  The reference's per-problem dynamic library
+ * (built by CmexTools' createGateway from the generated C, lib/cmex2optimizeCS.m:403-433)
+ * exports, with every argument passed by pointer:
+ *
+ *   void <class>_set_<name>(const double *input);              writeCfunctionpergroup.m:524
+ *   void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter,
+ *                       double *addEye2Hessian, int32_t *status, int32_t *iter,
+ *                       double *time);                          lib/ipmPD_CSsolver.c:132-141
+ *   void <class>_getOutputs(double *y1, double *y2, ...);       writeCfunctionpergroup.m:607-635
+ *
+ * and keeps ONE problem instance in process-global storage.  The entry points below are
+ * the same three operations on a handle that owns a BATCH of instances resident in the HBM
+ * of one GPU.  Plain pointers and sizes only; every function returns 0 on success, a
+ * negative TC_E* code for API misuse, or a positive cudaError_t.
+ *
+ * Array layout across this boundary: for a variable with n entries, a batch is
+ * `double[batch][n]` (instance-major; each instance column-major like MATLAB), i.e. a
+ * MATLAB array with the batch as trailing dimension.
+ */
+#ifndef TENSCALC_B200_H
+#define TENSCALC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tc_solver tc_solver;
+
+#define TC_EINVAL  (-1)  /* bad argument (index, batch size, null pointer) */
+#define TC_EFORMAT (-2)  /* problem image not recognised                   */
+#define TC_ENOGPU  (-3)  /* no CUDA device: there is no CPU fallback       */
+
+/* Library / device queries. */
+int tc_version(void);
+int tc_device_count(void);
+
+/* Create a solver for `batch` instances of the problem described by `image` (the compiled
+ * problem written by tenscalc_b200.tape.serialize; replaces loading <class>.so).  The
+ * handle owns all device memory; one CUDA stream per handle; handles are independent. */
+int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t batch, int device);
+int tc_destroy(tc_solver *s);
+
+/* Introspection (what the generated class's help text lists). */
+int64_t tc_batch(const tc_solver *s);
+int tc_num_sets(const tc_solver *s);      /* parameters first, then optimisation variables */
+int tc_num_outputs(const tc_solver *s);
+int64_t tc_set_size(const tc_solver *s, int set_index);
+int64_t tc_output_size(const tc_solver *s, int output_index);
+int64_t tc_scratch_bytes(const tc_solver *s);
+
+/* <class>_set_<name>: `values` is double[batch][n] on the host (tc_set) or on the device
+ * (tc_set_device).  With batch_stride==0 the same n values are broadcast to all instances. */
+int tc_set(tc_solver *s, int set_index, const double *values, int64_t batch_stride);
+int tc_set_device(tc_solver *s, int set_index, const double *d_values, int64_t batch_stride);
+
+/* ipmPD_CSsolver for every instance.  Inputs by pointer as in the reference; `status` and
+ * `iter` are int32[batch]; `time` receives the device time of the whole batch in seconds.
+ * tc_solve copies status/iter to host memory; tc_solve_device leaves them on the device and
+ * does not synchronise the host (`time` may be NULL). */
+int tc_solve(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+             const double *addEye2Hessian, int32_t *status, int32_t *iter, double *time);
+int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+                    const double *addEye2Hessian, int32_t *d_status, int32_t *d_iter);
+
+/* <class>_getOutputs: y[k] is double[batch][tc_output_size(k)], caller-allocated. */
+int tc_get_outputs(tc_solver *s, double *const *y);
+int tc_get_outputs_device(tc_solver *s, double *const *d_y);
+
+/* Stream control and measurement hooks used by bench.py. */
+int tc_synchronize(tc_solver *s);
+void *tc_stream(tc_solver *s);                 /* cudaStream_t of the handle */
+int tc_last_solve_ms(tc_solver *s, float *ms); /* CUDA-event time of the last solve kernel */
+int tc_kernel_launches(const tc_solver *s, int64_t *count);
+int tc_total_newton_steps(tc_solver *s, int64_t *steps); /* sum of iter over the batch */
+const char *tc_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSCALC_B200_H */

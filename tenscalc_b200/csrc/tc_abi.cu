@@ -1,0 +1,402 @@
+// C ABI of the batched interior-point backend (see include/tenscalc_b200.h) and the kernels
+// behind it.  Compiled for sm_100a only; there is no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/tenscalc_b200.h"
+#include "tc_driver.cuh"
+
+#define TC_BLOCK 128   // threads per CTA = instances per CTA; the stride is a multiple of it
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &P, int64_t inst) {
+    c.mb = P.m + inst;
+    c.stride = P.stride;
+    c.consts = P.consts;
+    c.tape = P.tape;
+    c.lane = threadIdx.x & 31u;
+    c.st[0] = P.group_status[inst];
+    c.st[1] = P.group_status[P.stride + inst];
+}
+
+__device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device_image &P, int64_t inst) {
+    P.group_status[inst] = c.st[0];
+    P.group_status[P.stride + inst] = c.st[1];
+}
+
+// whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
+__global__ void __launch_bounds__(TC_BLOCK) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
+                                                            double aeU, double aeEq,
+                                                            int32_t *__restrict__ status,
+                                                            int32_t *__restrict__ iter) {
+    const int64_t inst = (int64_t)blockIdx.x * TC_BLOCK + threadIdx.x;
+    const bool valid = inst < P.batch;
+    tc_lane c;
+    tc_lane_init(c, P, inst);
+    int st, it;
+    tc_ipm_solve(c, P, valid, mu0, maxIter, aeU, aeEq, st, it);
+    tc_lane_finish(c, P, inst);
+    if (valid) {
+        status[inst] = st;
+        iter[inst] = it;
+    }
+}
+
+// lazy evaluation of the parents of one get function (classname_getOutputs)
+__global__ void __launch_bounds__(TC_BLOCK) tc_eval_kernel(tc_device_image P, int fn) {
+    const int64_t inst = (int64_t)blockIdx.x * TC_BLOCK + threadIdx.x;
+    tc_lane c;
+    tc_lane_init(c, P, inst);
+    tc_get(c, P, fn, inst < P.batch);
+    tc_lane_finish(c, P, inst);
+}
+
+// classname_set_<name>: values[batch][n] -> m[slot_k][instance]  (32x32 tiles through smem so
+// that both the read and the write are coalesced), then groupStatus[children]=0
+__global__ void tc_set_kernel(tc_device_image P, int fn, const double *__restrict__ values,
+                              int64_t batch_stride) {
+    __shared__ double tile[32][33];
+    const tc_func f = P.funcs[fn];
+    const uint32_t n = f.io_cnt;
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const uint32_t k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // rows = instances, cols = entries
+        int64_t b = b0 + j;
+        uint32_t k = k0 + threadIdx.x;
+        if (b < P.batch && k < n) tile[j][threadIdx.x] = values[b * batch_stride + k];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // rows = entries, cols = instances
+        uint32_t k = k0 + j;
+        int64_t b = b0 + threadIdx.x;
+        if (b < P.batch && k < n) P.m[(size_t)P.io[f.io_off + k] * P.stride + b] = tile[threadIdx.x][j];
+    }
+    if (blockIdx.y == 0 && threadIdx.y == 0) {
+        int64_t b = b0 + threadIdx.x;
+        if (b < P.batch) {
+            P.group_status[b] &= ~f.children[0];
+            P.group_status[P.stride + b] &= ~f.children[1];
+        }
+    }
+}
+
+// gather of one output: m[src_k][instance] -> y[batch][n]
+__global__ void tc_gather_kernel(tc_device_image P, uint32_t io_off, uint32_t n, double *__restrict__ y) {
+    __shared__ double tile[32][33];
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const uint32_t k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        uint32_t k = k0 + j;
+        int64_t b = b0 + threadIdx.x;
+        if (b < P.batch && k < n) {
+            uint32_t w = P.io[io_off + k];
+            double v = 0.0;
+            if (w != TC_NO_SLOT)
+                v = (w & TC_CONST_BIT) ? P.consts[w & TC_SLOT_MASK] : P.m[(size_t)(w & TC_SLOT_MASK) * P.stride + b];
+            tile[j][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t b = b0 + j;
+        uint32_t k = k0 + threadIdx.x;
+        if (b < P.batch && k < n) y[b * (int64_t)n + k] = tile[threadIdx.x][j];
+    }
+}
+
+__global__ void tc_sum_iter_kernel(const int32_t *iter, int64_t n, unsigned long long *out) {
+    unsigned long long s = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += (unsigned long long)iter[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(TC_FULL, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct tc_solver {
+    int device = 0;
+    int64_t batch = 0, stride = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    tc_device_image img{};
+    std::vector<void *> allocs;
+    std::vector<tc_func> funcs;          // host copy
+    std::vector<uint32_t> set_fids, out_sizes, out_offs;
+    int32_t *d_status = nullptr, *d_iter = nullptr;
+    unsigned long long *d_sum = nullptr;
+    double *d_stage = nullptr;           // staging for host<->device I/O
+    size_t stage_bytes = 0;
+    int64_t n_slots = 0, launches = 0;
+    float last_ms = 0.f;
+};
+
+#define TC_CUDA(x)                           \
+    do {                                     \
+        cudaError_t e_ = (x);                \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+extern "C" {
+
+int tc_version(void) { return 100; }
+
+int tc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *tc_error_string(int code) {
+    switch (code) {
+    case 0: return "ok";
+    case TC_EINVAL: return "invalid argument";
+    case TC_EFORMAT: return "unrecognised problem image";
+    case TC_ENOGPU: return "no CUDA device (there is no CPU fallback)";
+    }
+    return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+}
+
+static int tc_upload(tc_solver *s, const void *src, size_t bytes, size_t pad_bytes, const void **dst) {
+    void *d = nullptr;
+    TC_CUDA(cudaMalloc(&d, bytes + pad_bytes + 8));
+    s->allocs.push_back(d);
+    TC_CUDA(cudaMemsetAsync(d, 0, bytes + pad_bytes + 8, s->stream));
+    TC_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s->stream));
+    *dst = d;
+    return 0;
+}
+
+int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t batch, int device) {
+    if (!out || !image || batch <= 0 || image_bytes < 64 * 8 + 16 * 8) return TC_EINVAL;
+    if (tc_device_count() <= device || device < 0) return TC_ENOGPU;
+    const int64_t *ih = (const int64_t *)image;
+    const double *dh = (const double *)(ih + 64);
+    if (ih[0] != TC_MAGIC) return TC_EFORMAT;
+    tc_solver *s = new (std::nothrow) tc_solver();
+    if (!s) return TC_EINVAL;
+    s->device = device;
+    s->batch = batch;
+    s->stride = (batch + TC_BLOCK - 1) / TC_BLOCK * TC_BLOCK;
+    const int64_t n_slots = ih[1], n_groups = ih[2], n_funcs = ih[3], n_sets = ih[4], n_out = ih[5],
+                  tape_words = ih[6], n_consts = ih[7], io_words = ih[8];
+    s->n_slots = n_slots;
+    auto pad8 = [](size_t b) { return (b + 7) / 8 * 8; };
+    const char *p = (const char *)(dh + 16);
+    const uint32_t *group_start = (const uint32_t *)p; p += pad8((n_groups + 1) * 4);
+    const uint32_t *tape = (const uint32_t *)p;        p += pad8(tape_words * 4);
+    const double *consts = (const double *)p;          p += pad8(n_consts * 8);
+    const tc_func *funcs = (const tc_func *)p;         p += pad8(n_funcs * sizeof(tc_func));
+    const uint32_t *io = (const uint32_t *)p;          p += pad8(io_words * 4);
+    const uint32_t *set_fids = (const uint32_t *)p;    p += pad8(n_sets * 4);
+    const uint32_t *out_sizes = (const uint32_t *)p;   p += pad8(n_out * 4);
+    if ((size_t)(p - (const char *)image) > image_bytes || n_groups > 128) { delete s; return TC_EFORMAT; }
+
+    int rc = 0;
+#define TC_TRY(x) do { rc = (x); if (rc) { tc_destroy(s); return rc; } } while (0)
+    TC_TRY((int)cudaSetDevice(device));
+    TC_TRY((int)cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    TC_TRY((int)cudaEventCreate(&s->ev0));
+    TC_TRY((int)cudaEventCreate(&s->ev1));
+    tc_device_image &I = s->img;
+    TC_TRY(tc_upload(s, group_start, (n_groups + 1) * 4, 0, (const void **)&I.group_start));
+    TC_TRY(tc_upload(s, tape, tape_words * 4, 64 * 4, (const void **)&I.tape));   // reader prefetches a window
+    TC_TRY(tc_upload(s, consts, n_consts * 8, 0, (const void **)&I.consts));
+    TC_TRY(tc_upload(s, funcs, n_funcs * sizeof(tc_func), 0, (const void **)&I.funcs));
+    TC_TRY(tc_upload(s, io, io_words * 4, 0, (const void **)&I.io));
+    void *d = nullptr;
+    const size_t mbytes = (size_t)n_slots * (size_t)s->stride * sizeof(double);
+    TC_TRY((int)cudaMalloc(&d, mbytes));
+    s->allocs.push_back(d);
+    I.m = (double *)d;
+    TC_TRY((int)cudaMemsetAsync(d, 0, mbytes, s->stream));
+    TC_TRY((int)cudaMalloc(&d, 2 * s->stride * sizeof(uint64_t)));
+    s->allocs.push_back(d);
+    I.group_status = (uint64_t *)d;
+    TC_TRY((int)cudaMemsetAsync(d, 0, 2 * s->stride * sizeof(uint64_t), s->stream));
+    TC_TRY((int)cudaMalloc(&d, s->stride * sizeof(int32_t) * 2 + 16));
+    s->allocs.push_back(d);
+    s->d_status = (int32_t *)d;
+    s->d_iter = s->d_status + s->stride;
+    s->d_sum = (unsigned long long *)(s->d_iter + s->stride);
+    I.stride = s->stride;
+    I.batch = batch;
+    I.n_groups = (int32_t)n_groups;
+    tc_defines &D = I.def;
+    D.nU = (int32_t)ih[16]; D.nG = (int32_t)ih[17]; D.nF = (int32_t)ih[18];
+    D.scaleCost = (int32_t)ih[19]; D.scaleInequalities = (int32_t)ih[20]; D.coupledAlphas = (int32_t)ih[21];
+    D.setAddEye2Hessian = (int32_t)ih[22]; D.adjustAddEye2Hessian = (int32_t)ih[23];
+    D.useInertia = (int32_t)ih[24]; D.skipAffine = (int32_t)ih[25]; D.delta = (int32_t)ih[26];
+    D.gradTolerance = dh[0]; D.addEye2HessianUtolerance = dh[1]; D.equalTolerance = dh[2];
+    D.desiredDualityGap = dh[3]; D.alphaMin = dh[4]; D.alphaMax = dh[5];
+    D.muFactorAggressive = dh[6]; D.muFactorConservative = dh[7];
+    if (D.useInertia || !D.skipAffine) { tc_destroy(s); return TC_EFORMAT; }
+    s->funcs.assign(funcs, funcs + n_funcs);
+    s->set_fids.assign(set_fids, set_fids + n_sets);
+    s->out_sizes.assign(out_sizes, out_sizes + n_out);
+    uint32_t off = s->funcs[FN_getOutputs].io_off;
+    size_t max_io = 1;
+    for (int64_t k = 0; k < n_out; k++) {
+        s->out_offs.push_back(off);
+        off += out_sizes[k];
+        if (out_sizes[k] > max_io) max_io = out_sizes[k];
+    }
+    for (int64_t k = 0; k < n_sets; k++)
+        if (s->funcs[set_fids[k]].io_cnt > max_io) max_io = s->funcs[set_fids[k]].io_cnt;
+    s->stage_bytes = max_io * (size_t)batch * sizeof(double);
+    TC_TRY((int)cudaMalloc(&d, s->stage_bytes));
+    s->allocs.push_back(d);
+    s->d_stage = (double *)d;
+    TC_TRY((int)cudaStreamSynchronize(s->stream));
+#undef TC_TRY
+    *out = s;
+    return 0;
+}
+
+int tc_destroy(tc_solver *s) {
+    if (!s) return TC_EINVAL;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+int64_t tc_batch(const tc_solver *s) { return s ? s->batch : TC_EINVAL; }
+int tc_num_sets(const tc_solver *s) { return s ? (int)s->set_fids.size() : TC_EINVAL; }
+int tc_num_outputs(const tc_solver *s) { return s ? (int)s->out_sizes.size() : TC_EINVAL; }
+int64_t tc_set_size(const tc_solver *s, int i) {
+    if (!s || i < 0 || i >= (int)s->set_fids.size()) return TC_EINVAL;
+    return s->funcs[s->set_fids[i]].io_cnt;
+}
+int64_t tc_output_size(const tc_solver *s, int i) {
+    if (!s || i < 0 || i >= (int)s->out_sizes.size()) return TC_EINVAL;
+    return s->out_sizes[i];
+}
+int64_t tc_scratch_bytes(const tc_solver *s) {
+    return s ? (int64_t)((size_t)s->n_slots * (size_t)s->stride * sizeof(double)) : TC_EINVAL;
+}
+void *tc_stream(tc_solver *s) { return s ? (void *)s->stream : nullptr; }
+
+int tc_set_device(tc_solver *s, int i, const double *d_values, int64_t batch_stride) {
+    if (!s || !d_values || i < 0 || i >= (int)s->set_fids.size()) return TC_EINVAL;
+    TC_CUDA(cudaSetDevice(s->device));
+    const uint32_t fn = s->set_fids[i];
+    const uint32_t n = s->funcs[fn].io_cnt;
+    dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
+    tc_set_kernel<<<grid, block, 0, s->stream>>>(s->img, (int)fn, d_values, batch_stride);
+    s->launches++;
+    return (int)cudaGetLastError();
+}
+
+int tc_set(tc_solver *s, int i, const double *values, int64_t batch_stride) {
+    if (!s || !values || i < 0 || i >= (int)s->set_fids.size()) return TC_EINVAL;
+    TC_CUDA(cudaSetDevice(s->device));
+    const size_t n = s->funcs[s->set_fids[i]].io_cnt;
+    const size_t bytes = (batch_stride == 0 ? n : n * (size_t)s->batch) * sizeof(double);
+    if (batch_stride != 0 && batch_stride != (int64_t)n) return TC_EINVAL;   // host batches are dense
+    TC_CUDA(cudaMemcpyAsync(s->d_stage, values, bytes, cudaMemcpyHostToDevice, s->stream));
+    return tc_set_device(s, i, s->d_stage, batch_stride);
+}
+
+int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+                    const double *addEye2Hessian, int32_t *d_status, int32_t *d_iter) {
+    if (!s || !mu0 || !maxIter || !addEye2Hessian || !d_status || !d_iter) return TC_EINVAL;
+    (void)saveIter;   // allowSave is a code-generation-time option of the reference (cmex2optimizeCS.m:326)
+    TC_CUDA(cudaSetDevice(s->device));
+    TC_CUDA(cudaEventRecord(s->ev0, s->stream));
+    tc_solve_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(
+        s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter);
+    s->launches++;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return 0;
+}
+
+int tc_solve(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+             const double *addEye2Hessian, int32_t *status, int32_t *iter, double *time) {
+    if (!s || !status || !iter) return TC_EINVAL;
+    int rc = tc_solve_device(s, mu0, maxIter, saveIter, addEye2Hessian, s->d_status, s->d_iter);
+    if (rc) return rc;
+    TC_CUDA(cudaMemcpyAsync(status, s->d_status, s->batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaMemcpyAsync(iter, s->d_iter, s->batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    TC_CUDA(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    if (time) *time = 1e-3 * (double)s->last_ms;
+    return 0;
+}
+
+int tc_get_outputs_device(tc_solver *s, double *const *d_y) {
+    if (!s || !d_y) return TC_EINVAL;
+    TC_CUDA(cudaSetDevice(s->device));
+    tc_eval_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(s->img, (int)FN_getOutputs);
+    s->launches++;
+    for (size_t k = 0; k < s->out_sizes.size(); k++) {
+        const uint32_t n = s->out_sizes[k];
+        dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
+        tc_gather_kernel<<<grid, block, 0, s->stream>>>(s->img, s->out_offs[k], n, d_y[k]);
+        s->launches++;
+    }
+    return (int)cudaGetLastError();
+}
+
+int tc_get_outputs(tc_solver *s, double *const *y) {
+    if (!s || !y) return TC_EINVAL;
+    TC_CUDA(cudaSetDevice(s->device));
+    tc_eval_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(s->img, (int)FN_getOutputs);
+    s->launches++;
+    for (size_t k = 0; k < s->out_sizes.size(); k++) {
+        const uint32_t n = s->out_sizes[k];
+        dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
+        tc_gather_kernel<<<grid, block, 0, s->stream>>>(s->img, s->out_offs[k], n, s->d_stage);
+        s->launches++;
+        TC_CUDA(cudaMemcpyAsync(y[k], s->d_stage, (size_t)n * s->batch * sizeof(double), cudaMemcpyDeviceToHost,
+                                s->stream));
+    }
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return (int)cudaGetLastError();
+}
+
+int tc_synchronize(tc_solver *s) {
+    if (!s) return TC_EINVAL;
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int tc_last_solve_ms(tc_solver *s, float *ms) {
+    if (!s || !ms) return TC_EINVAL;
+    TC_CUDA(cudaEventSynchronize(s->ev1));
+    TC_CUDA(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    *ms = s->last_ms;
+    return 0;
+}
+
+int tc_kernel_launches(const tc_solver *s, int64_t *count) {
+    if (!s || !count) return TC_EINVAL;
+    *count = s->launches;
+    return 0;
+}
+
+int tc_total_newton_steps(tc_solver *s, int64_t *steps) {
+    if (!s || !steps) return TC_EINVAL;
+    TC_CUDA(cudaSetDevice(s->device));
+    TC_CUDA(cudaMemsetAsync(s->d_sum, 0, sizeof(unsigned long long), s->stream));
+    tc_sum_iter_kernel<<<148, 256, 0, s->stream>>>(s->d_iter, s->batch, s->d_sum);
+    s->launches++;
+    unsigned long long h = 0;
+    TC_CUDA(cudaMemcpyAsync(&h, s->d_sum, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaStreamSynchronize(s->stream));
+    *steps = (int64_t)h;
+    return 0;
+}
+
+}  // extern "C"

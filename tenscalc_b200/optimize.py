@@ -1,0 +1,152 @@
+"""``cmex2optimizeCS`` -- generate a batched interior-point solver for
+
+        minimise  objective(u)   s.t.  G(u)=0,  F(u)>=0
+
+Mirrors the name/value surface of the reference generator
+(``lib/cmex2optimizeCS.m:1-52``; defaults ``lib/private/parameters4all.m`` and
+``parameters4optimize.m``) and its sequence of declarations (:156-355): sets for
+parameters and optimisation variables, ``parseConstraints`` (private/parseConstraints.m:72-132),
+primal/dual packing (private/packVariables.m:38-70), ``initPrimal__``, the
+``ipmPD_CStimesLambda`` builder, the ``#define`` table handed to the driver (:303-331)
+and ``getOutputs``.
+
+The returned :class:`GeneratedSolver` plays the role of the generated class: calling it
+creates an object with ``setP_<name>/setV_<name>/solve/getOutputs`` working on a whole
+batch of instances on one GPU (``runtime.BatchedSolver``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import tensor as T
+from .csparse import CSparse, CompiledProblem
+from .ipm_builder import build_ipm_timeslambda
+from .tensor import Constraint, Tcalculus
+
+
+@dataclass
+class GeneratedSolver:
+    classname: str
+    problem: CompiledProblem
+    parameters: List[Tuple[str, Tuple[int, ...]]]
+    variables: List[Tuple[str, Tuple[int, ...]]]
+    outputs: List[Tuple[str, Tuple[int, ...]]]
+    output_is_struct: bool
+    defines: Dict[str, object]
+    info: Dict[str, object] = field(default_factory=dict)
+
+    def __call__(self, batch: int = 1, device: Optional[int] = None):
+        from .runtime import BatchedSolver
+        return BatchedSolver(self, batch, device)
+
+
+def _name_of(v: Tcalculus) -> str:
+    if not v.is_variable():
+        raise ValueError("parameters and optimizationVariables must be Tvariables")
+    return v.name
+
+
+def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
+                    optimizationVariables: Sequence[Tcalculus],
+                    constraints: Sequence[Constraint] = (),
+                    outputExpressions: Union[Sequence[Tcalculus], Dict[str, Tcalculus]] = (),
+                    parameters: Sequence[Tcalculus] = (),
+                    gradTolerance: float = 1e-4, equalTolerance: float = 1e-4,
+                    desiredDualityGap: float = 1e-5, alphaMin: float = 1e-7, alphaMax: float = 1.0,
+                    coupledAlphas: bool = True, muFactorAggressive: float = .2,
+                    muFactorConservative: float = .95, skipAffine: bool = True, delta: int = 3,
+                    scaleInequalities: bool = True, scaleCost: float = 0.0,
+                    scaleEqualities: bool = False, addEye2Hessian: bool = True,
+                    adjustAddEye2Hessian: bool = True, useInertia: bool = False,
+                    addEye2HessianUtolerance: float = 1e-6, useLDL: bool = True,
+                    smallerNewtonMatrix: bool = False, useUmfpack: bool = False,
+                    sensitivityVariables: Sequence[Tcalculus] = (),
+                    solverVerboseLevel: int = 1, ordering=None, **ignored) -> GeneratedSolver:
+    # the reference's C generator hard-wires algorithm 3 and rejects the options below
+    # (cmex2optimizeCS.m:83-93, ipmPD_CStimesLambda.m:31-48)
+    if sensitivityVariables:
+        raise NotImplementedError("sensitivityVariables: not implemented by ipmPD_CStimesLambda")
+    if smallerNewtonMatrix:
+        raise NotImplementedError("smallerNewtonMatrix=true: not implemented by ipmPD_CStimesLambda")
+    if not useLDL or useUmfpack:
+        raise NotImplementedError("useLDL=false/useUmfpack=true: not implemented by ipmPD_CStimesLambda")
+    skipAffine = True
+
+    tab = T.table()
+    code = CSparse(tab)
+    if objective.numel() != 1:
+        raise ValueError("objective must be a scalar")
+
+    # ---- sets for parameters and optimisation variables (:156-195) -----------------------
+    par_info = []
+    for p in parameters:
+        nm = _name_of(p)
+        code.declare_set(f"setP_{nm}", p.flat(), p.shape, kind="parameter")
+        par_info.append((nm, p.shape))
+    # The symbolic variables themselves become the packed primal vector u (the reference
+    # substitutes them by slices of a new variable `x_`, packVariables.m:38-70); setV_*
+    # writes separate storage that initPrimal__ copies into u (:216-218).
+    u: List[int] = []
+    u0: List[int] = []
+    var_info = []
+    for v in optimizationVariables:
+        nm = _name_of(v)
+        ids = v.flat()
+        store = [tab.new_set(f"{nm}_init[{k}]") for k in range(len(ids))]
+        code.declare_set(f"setV_{nm}", store, v.shape, kind="variable")
+        u += ids
+        u0 += store
+        var_info.append((nm, v.shape))
+    if len(set(u)) != len(u):
+        raise ValueError("optimizationVariables must be distinct")
+    code.declare_copy("initPrimal__", u, u0)
+
+    # ---- constraints -> G (==0), F (>=0) and dual variables (parseConstraints.m:72-132) -----
+    G: List[Optional[int]] = []
+    F: List[Optional[int]] = []
+    for c in constraints:
+        if not isinstance(c, Constraint):
+            raise ValueError("constraint is not a Tcalculus comparison")
+        (G if c.kind == "iszero" else F).extend(c.expr.flat())
+    nu = [tab.new_set(f"nu__[{k}]") for k in range(len(G))]
+    lam = [tab.new_set(f"lambda__[{k}]") for k in range(len(F))]
+
+    info = build_ipm_timeslambda(code, u, objective.e[()], F, G, lam, nu,
+                                 scaleInequalities=scaleInequalities, scaleCost=scaleCost,
+                                 addEye2Hessian=addEye2Hessian, useInertia=useInertia,
+                                 ordering=ordering)
+
+    # ---- outputs (:337-355) --------------------------------------------------------------------
+    is_struct = isinstance(outputExpressions, dict)
+    items = list(outputExpressions.items()) if is_struct else \
+        [(f"y{k + 1}", e) for k, e in enumerate(outputExpressions)]
+    out_info = []
+    srcs, shapes, names = [], [], []
+    for nm, e in items:
+        e = Tcalculus._lift(e)
+        srcs.append(e.flat())
+        shapes.append(e.shape)
+        names.append(nm)
+        out_info.append((nm, e.shape))
+    code.declare_get("getOutputs", srcs, shapes, names)
+
+    defines = dict(
+        nU=len(u), nG=len(G), nF=len(F),
+        gradTolerance=float(gradTolerance), addEye2HessianUtolerance=float(addEye2HessianUtolerance),
+        equalTolerance=float(equalTolerance), desiredDualityGap=float(desiredDualityGap),
+        scaleCost=int(scaleCost != 0), scaleInequalities=int(bool(scaleInequalities)),
+        scaleEqualities=int(bool(scaleEqualities)),
+        alphaMin=float(alphaMin), alphaMax=float(alphaMax), coupledAlphas=int(bool(coupledAlphas)),
+        setAddEye2Hessian=int(bool(addEye2Hessian)), adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)),
+        useInertia=int(bool(useInertia)), muFactorAggressive=float(muFactorAggressive),
+        muFactorConservative=float(muFactorConservative), delta=int(delta), skipAffine=int(skipAffine),
+        smallerNewtonMatrix=0, useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0,
+        profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
+    problem = code.compile(defines)
+    fac = info["factor"]
+    gen_info = dict(nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
+                    n_groups=len(problem.groups), n_slots=problem.n_slots)
+    return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)

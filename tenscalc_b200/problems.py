@@ -1,0 +1,228 @@
+"""Problem definitions of the BASELINE configurations, transcribed from the reference's
+example scripts into the Python front end (same variables, constraints, options).
+
+* ``sls``            examples/sls.m:136-166 (box-constrained least squares; README.md:166-187)
+* ``l1l2``           examples/l1l2estimationCS.m:137-183
+* ``mpc_dcmotor``    examples/mpcmhe/mpc_dcmotor.m:52-142
+* ``mpc_quadcopter`` examples/mpcmhe/mpc_quadcopter.m:86-182
+
+Each builder returns a :class:`~tenscalc_b200.optimize.GeneratedSolver` plus the solve
+arguments the script uses (``mu0``, ``maxIter``).  ``synthetic_inputs`` draws the
+seeded parameter/initial-value batches described in SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+
+from . import tensor as T
+from .optimize import GeneratedSolver, cmex2optimizeCS
+from .tensor import (Tconstant, Tones, Tvariable, Tzeros, horzcat, norm2, repmat, reshape, sqrt,
+                     tmax, tmin, tsCross, tsDerivative, tsDerivative2, tsIntegral, tsum, vertcat)
+
+
+def sls(N: int = 100, n: int = 8, **opts) -> Tuple[GeneratedSolver, dict]:
+    T.clear()
+    A = Tvariable("A", [N, n])
+    b = Tvariable("b", N)
+    x = Tvariable("x", n)
+    y = A @ x - b
+    J = norm2(y) / N
+    gen = cmex2optimizeCS(classname="tmp_minslsc2", objective=J, optimizationVariables=[x],
+                          constraints=[x >= 0, x <= .05], outputExpressions=[J, x],
+                          parameters=[A, b], **opts)
+    return gen, dict(mu0=1.0, maxIter=30)
+
+
+def l1l2(N: int = 200, **opts) -> Tuple[GeneratedSolver, dict]:
+    T.clear()
+    measurement = Tvariable("measurement", N)
+    dt1 = Tvariable("dt1", N - 1)
+    weight2acceleration = Tvariable("weight2acceleration", ())
+    position = Tvariable("position", N)
+    weight1acceleration = Tvariable("weight1acceleration", ())
+    weight1noise = Tvariable("weight1noise", ())
+    noise1 = Tvariable("noise1", N)
+    acceleration1 = Tvariable("acceleration1", N - 2)
+    noise1abs = Tvariable("noise1abs", N)
+    acceleration1abs = Tvariable("acceleration1abs", N - 2)
+
+    velocity = (position[1:] - position[:-1]) * dt1
+    acceleration = (velocity[1:] - velocity[:-1]) * dt1[:-1]
+    noise2 = measurement - position - noise1
+    acceleration2 = acceleration - acceleration1
+    J = (norm2(noise2) + weight2acceleration * norm2(acceleration2)
+         + weight1noise * tsum(noise1abs, 0) + weight1acceleration * tsum(acceleration1abs, 0))
+    o = dict(scaleCost=1, desiredDualityGap=1e-3)
+    o.update(opts)
+    gen = cmex2optimizeCS(
+        classname="tmpC_minl1l2", objective=J,
+        optimizationVariables=[position, noise1, acceleration1, noise1abs, acceleration1abs],
+        constraints=[noise1 <= noise1abs, noise1 >= -noise1abs,
+                     acceleration1 <= acceleration1abs, acceleration1 >= -acceleration1abs],
+        outputExpressions=[J, position, noise1, acceleration1, noise1abs, acceleration1abs],
+        parameters=[measurement, dt1, weight1acceleration, weight2acceleration, weight1noise], **o)
+    return gen, dict(mu0=1.0, maxIter=100)
+
+
+def mpc_dcmotor(T_: int = 30, **opts) -> Tuple[GeneratedSolver, dict]:
+    T.clear()
+    nX, nU = 2, 1
+    Ts = Tvariable("Ts", ())
+    x = Tvariable("x", [nX, T_])
+    u = Tvariable("u", [nU, T_ - 1])
+    xinit = Tvariable("xinit", [nX, 1])
+    p = Tvariable("p", ())
+    k = Tvariable("k", ())
+    A = vertcat(horzcat(Tzeros(1, 1), Tones(1, 1)), horzcat(Tzeros(1, 1), reshape(p, (1, 1))))
+    B = vertcat(Tzeros(1, 1), reshape(k, (1, 1)))
+    dynamics = [x[:, 1:] == x[:, :-1] + Ts * (A @ x[:, :-1] + B @ u),
+                x[:, 0:1] == xinit]
+    min_x = Tvariable("min_x", [nX, 1])
+    max_x = Tvariable("max_x", [nX, 1])
+    min_u = Tvariable("min_u", [nU, 1])
+    max_u = Tvariable("max_u", [nU, 1])
+    constraints = [x[:, 1:] >= repmat(min_x, [1, T_ - 1]),
+                   x[:, 1:] <= repmat(max_x, [1, T_ - 1]),
+                   u >= repmat(min_u, [1, T_ - 1]),
+                   u <= repmat(max_u, [1, T_ - 1])]
+    ref = Tvariable("ref", [1, T_])
+    lambda_u = Tvariable("lambda_u", ())
+    Jx2 = tsIntegral(tsum((x[0:1, :] - ref) ** 2, 0), Ts)
+    Ju2 = tsIntegral(tsum(u ** 2, 0), Ts)
+    J = Jx2 + lambda_u * Ju2
+    uWarm = horzcat(u[:, 1:], Tzeros(nU, 1))
+    xWarm = x[:, list(range(1, T_)) + [T_ - 1]]
+    xWarm = tmax(xWarm, repmat(min_x + .05 * (max_x - min_x), [1, T_]))
+    xWarm = tmin(xWarm, repmat(max_x - .05 * (max_x - min_x), [1, T_]))
+    uWarm = tmax(uWarm, repmat(min_u + .05 * (max_u - min_u), [1, T_ - 1]))
+    uWarm = tmin(uWarm, repmat(max_u - .05 * (max_u - min_u), [1, T_ - 1]))
+    outputs = dict(J=J, Jx2=Jx2, Ju2=Ju2, t=Tconstant(np.arange(T_)) * Ts, u=u, x=x, ref=ref,
+                   xWarm=xWarm, uWarm=uWarm)
+    gen = cmex2optimizeCS(classname="tmp_mpc_dcmotor", objective=J, optimizationVariables=[u, x],
+                          constraints=dynamics + constraints, outputExpressions=outputs,
+                          parameters=[Ts, p, k, xinit, ref, min_x, max_x, min_u, max_u, lambda_u],
+                          addEye2Hessian=True, adjustAddEye2Hessian=True, scaleInequalities=True, **opts)
+    return gen, dict(mu0=1e-3, maxIter=100)
+
+
+def mpc_quadcopter(T_: int = 100, **opts) -> Tuple[GeneratedSolver, dict]:
+    T.clear()
+    Ts = Tvariable("Ts", ())
+    p = Tvariable("p", [3, T_])
+    u = Tvariable("u", [3, T_])
+    pinit = Tvariable("pinit", [3, 1])
+    vinit = Tvariable("vinit", [3, 1])
+    b_drag = Tvariable("b_drag", ())
+    g = Tconstant([[0], [0], [9.8]])
+    min_thrust = Tvariable("min_thrust", ())
+    max_thrust = Tvariable("max_thrust", ())
+    min_altitude = Tvariable("min_altitude", ())
+    v = tsDerivative(p, Ts)
+    a = tsDerivative2(p, Ts)
+    dynamics = [a == -b_drag * v + repmat(g, [1, T_]) + u,
+                p[:, 0:1] == pinit,
+                v[:, 0:1] == vinit]
+    m_thrust = sqrt(tsum(u ** 2, 0))                       # size [T]
+    R_ib3 = u / repmat(reshape(m_thrust, [1, T_]), [3, 1])
+    R_ib2 = tsCross(R_ib3, vertcat(Tzeros(2, T_), Tones(1, T_)))
+    R_ib1 = tsCross(R_ib2, R_ib3)
+    positive2 = Tvariable("positive2", [T_])
+    constraints = [m_thrust >= min_thrust,
+                   max_thrust - m_thrust == positive2,
+                   positive2 > 0,
+                   p[2, :] < -min_altitude]
+    pdesired = Tvariable("pdesired", [3, 1])
+    vdesired = Tvariable("vdesired", [3, 1])
+    lambda_v = Tvariable("lambda_v", ())
+    lambda_thrust = Tvariable("lambda_thrust", ())
+    Jp2 = tsIntegral(tsum((p - repmat(pdesired, [1, T_])) ** 2, 0), Ts)
+    Jv2 = tsIntegral(tsum((v - repmat(vdesired, [1, T_])) ** 2, 0), Ts)
+    Jthrust = tsIntegral(m_thrust, Ts)
+    J = Jp2 + lambda_v * Jv2 + lambda_thrust * Jthrust
+    outputs = dict(J=J, Jp2=Jp2, Jv2=Jv2, Jthrust=Jthrust, t=Tconstant(np.arange(T_)) * Ts, u=u,
+                   m_thrust=m_thrust, p=p, v=v, a=a, R_ib1=R_ib1, R_ib2=R_ib2, R_ib3=R_ib3,
+                   positive2=positive2)
+    gen = cmex2optimizeCS(classname="tmp_quadcopter", objective=J,
+                          optimizationVariables=[p, u, positive2],
+                          constraints=dynamics + constraints, outputExpressions=outputs,
+                          parameters=[Ts, pinit, vinit, pdesired, vdesired, b_drag, min_thrust,
+                                      max_thrust, min_altitude, lambda_v, lambda_thrust],
+                          addEye2Hessian=True, adjustAddEye2Hessian=True, scaleInequalities=True, **opts)
+    return gen, dict(mu0=1e-3, maxIter=1000)
+
+
+BUILDERS = dict(sls=sls, l1l2=l1l2, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic batches; arrays carry the batch as the LAST dimension
+# ------------------------------------------------------------------------------------------------
+def synthetic_inputs(name: str, gen: GeneratedSolver, batch: int, seed: int = 0) -> Tuple[Dict, Dict]:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    B = batch
+    if name == "sls":
+        N, n = dict(gen.parameters)["A"]
+        P = dict(A=rng.random((N, n, B)), b=rng.random((N, B)))
+        V = dict(x=.02 * rng.random((n, B)))
+    elif name == "l1l2":
+        N = dict(gen.parameters)["measurement"][0]
+        t = np.cumsum(np.ceil(rng.random((N, B)) * 3), axis=0)     # irregular sample times
+        true_pos = 5 * np.sin(np.abs(t - 100) / 5)
+        meas = np.round(true_pos + rng.standard_normal((N, B)))
+        outl = rng.random((N, B)) < .1
+        meas[outl] = np.round(10 * rng.standard_normal(int(outl.sum())))
+        P = dict(measurement=meas, dt1=1. / np.diff(t, axis=0),
+                 weight1acceleration=np.ones(B), weight2acceleration=10 * np.ones(B),
+                 weight1noise=np.ones(B))
+        V = dict(position=rng.random((N, B)), noise1=rng.random((N, B)),
+                 acceleration1=rng.random((N - 2, B)), noise1abs=10 * np.ones((N, B)),
+                 acceleration1abs=10 * np.ones((N - 2, B)))
+    elif name == "mpc_dcmotor":
+        T_ = dict(gen.parameters)["ref"][1]
+        Ts = .1
+        xinit = np.stack([rng.uniform(-.35, .35, B), rng.uniform(-.25, .25, B)])[:, None, :]
+        t0 = rng.uniform(0, 4 * np.pi, B)
+        tt = t0[None, :] + Ts * np.arange(T_)[:, None]
+        ref = (-.35 * np.sign(np.sin(.5 * tt)))[None, :, :]
+        ones = np.ones(B)
+        P = dict(Ts=Ts * ones, p=-2 * ones, k=ones, xinit=xinit, ref=ref,
+                 min_x=np.array([-.4, -.3])[:, None, None] * ones, max_x=np.array([.4, .3])[:, None, None] * ones,
+                 min_u=-ones[None, None, :], max_u=ones[None, None, :], lambda_u=ones / 50)
+        V = dict(x=xinit + .01 * rng.random((2, T_, B)), u=.01 * rng.random((1, T_ - 1, B)))
+    elif name == "mpc_quadcopter":
+        T_ = dict(gen.variables)["p"][1]
+        Ts, b_drag = .02, .1
+        ones = np.ones(B)
+        pinit = rng.normal(0, .5, (3, B))
+        pinit[2] = np.minimum(pinit[2], -.2)
+        vinit = rng.normal(0, .3, (3, B))
+        pdes = np.array([0, 5., -2.5])[:, None] * ones
+        P = dict(Ts=Ts * ones, pinit=pinit[:, None, :], vinit=vinit[:, None, :],
+                 pdesired=pdes[:, None, :], vdesired=np.zeros((3, 1, B)), b_drag=b_drag * ones,
+                 min_thrust=5 * ones, max_thrust=20 * ones, min_altitude=-.1 * ones,
+                 lambda_v=.05 * ones, lambda_thrust=.05 * ones)
+        # primal initialisation (mpc_quadcopter.m:234-247): cubic through p(t1), p(t1)+Ts v,
+        # p(t1)+2Ts v and the partial goal at t_T (not-a-knot spline over 4 points = the
+        # interpolating cubic)
+        pfinal = pinit + (pdes - pinit) / 10
+        tk = np.array([1, 2, 3, T_]) * Ts
+        tq = np.arange(1, T_ + 1) * Ts
+        vals = np.stack([pinit, pinit + Ts * vinit, pinit + 2 * Ts * vinit, pfinal])      # [4,3,B]
+        Vm = np.vander(tk, 4)
+        coef = np.linalg.solve(Vm, vals.reshape(4, -1))
+        p = (np.vander(tq, 4) @ coef).reshape(T_, 3, B).transpose(1, 0, 2)
+        v = np.empty_like(p)
+        v[:, 0] = (-1.5 * p[:, 0] + 2 * p[:, 1] - .5 * p[:, 2]) / Ts
+        v[:, 1:-1] = -.5 / Ts * (p[:, :-2] - p[:, 2:])
+        v[:, -1] = (.5 * p[:, -3] - 2 * p[:, -2] + 1.5 * p[:, -1]) / Ts
+        a = np.empty_like(p)
+        a[:, 1:-1] = (p[:, :-2] - 2 * p[:, 1:-1] + p[:, 2:]) / Ts ** 2
+        a[:, 0] = a[:, 1]
+        a[:, -1] = a[:, -2]
+        u = a + b_drag * v - np.array([0, 0, 9.8])[:, None, None]
+        V = dict(p=p, u=u, positive2=np.ones((T_, B)))
+    else:
+        raise KeyError(name)
+    return P, V

@@ -1,0 +1,193 @@
+"""Batched counterpart of the class the reference generates
+(``obj=classname(); setP_*(obj,v); setV_*(obj,v); [status,iter,time]=solve(obj,mu0,maxIter,
+saveIter,addEye2Hessian); y=getOutputs(obj)`` -- lib/cmex2optimizeCS.m:280-294,
+doc/sphinx/optimization.rst:487-556), bound to the C ABI of ``include/tenscalc_b200.h``
+through ctypes.  Every array carries the batch as trailing dimension.
+
+There is no CPU fallback: constructing a solver without the native library or without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import tape
+from .build import LIB
+from .optimize import GeneratedSolver
+
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+# every symbol include/tenscalc_b200.h declares: (name, restype, argtypes)
+ABI = [
+    ("tc_version", ctypes.c_int, []),
+    ("tc_device_count", ctypes.c_int, []),
+    ("tc_create", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_size_t,
+                                 ctypes.c_int64, ctypes.c_int]),
+    ("tc_destroy", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_batch", ctypes.c_int64, [ctypes.c_void_p]),
+    ("tc_num_sets", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_num_outputs", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_set_size", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
+    ("tc_output_size", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
+    ("tc_scratch_bytes", ctypes.c_int64, [ctypes.c_void_p]),
+    ("tc_set", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
+    ("tc_set_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
+    ("tc_solve", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p, _dp]),
+    ("tc_solve_device", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p]),
+    ("tc_get_outputs", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    ("tc_get_outputs_device", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    ("tc_synchronize", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_stream", ctypes.c_void_p, [ctypes.c_void_p]),
+    ("tc_last_solve_ms", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    ("tc_kernel_launches", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    ("tc_total_newton_steps", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    ("tc_error_string", ctypes.c_char_p, [ctypes.c_int]),
+]
+
+
+def load_library():
+    """dlopen the in-tree native library and bind the ABI; fails loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"native library {LIB} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(LIB)
+        for name, res, args in ABI:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class TenscalcError(RuntimeError):
+    pass
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise TenscalcError(f"tenscalc_b200: {load_library().tc_error_string(rc).decode()} (code {rc})")
+
+
+class BatchedSolver:
+    def __init__(self, gen: GeneratedSolver, batch: int, device: Optional[int] = None):
+        lib = load_library()
+        if lib.tc_device_count() == 0:
+            raise TenscalcError("no CUDA device visible: the batched solver has no CPU path")
+        self.gen = gen
+        self.batch = int(batch)
+        self.device = int(device if device is not None else os.environ.get("LOCAL_RANK", 0))
+        self._image = tape.serialize(gen)
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(self._image, len(self._image))
+        _check(lib.tc_create(ctypes.byref(h), buf, len(self._image), self.batch, self.device))
+        self._h = h
+        self._lib = lib
+        self._set_index: Dict[str, int] = {}
+        for k, (n, _) in enumerate(gen.parameters):
+            self._set_index["P_" + n] = k
+        for k, (n, _) in enumerate(gen.variables):
+            self._set_index["V_" + n] = len(gen.parameters) + k
+        self._shapes = {("P_" + n): s for n, s in gen.parameters}
+        self._shapes.update({("V_" + n): s for n, s in gen.variables})
+
+    # -- reference surface ---------------------------------------------------------------------
+    def __getattr__(self, name: str):
+        if name.startswith("setP_") or name.startswith("setV_"):
+            key = name[3:]
+            if key in self.__dict__.get("_set_index", {}):
+                return lambda value: self._set(key, value)
+        raise AttributeError(name)
+
+    def _set(self, key: str, value) -> None:
+        shape = tuple(self._shapes[key])
+        n = int(np.prod(shape)) if shape else 1
+        idx = self._set_index[key]
+        if hasattr(value, "data_ptr"):                       # torch CUDA tensor [batch, n], zero-copy
+            if not value.is_cuda or value.dtype.itemsize != 8 or not value.is_contiguous():
+                raise TenscalcError("device values must be contiguous float64 CUDA tensors")
+            if value.numel() != n * self.batch:
+                raise TenscalcError(f"{key}: expected {n}x{self.batch} values")
+            import torch
+            torch.cuda.current_stream(value.device).synchronize()
+            _check(self._lib.tc_set_device(self._h, idx, ctypes.c_void_p(value.data_ptr()), n))
+            return
+        a = np.asarray(value, dtype=np.float64)
+        if a.shape == shape:                                 # one value for the whole batch
+            flat = np.ascontiguousarray(a.reshape(-1, order="F"))
+            _check(self._lib.tc_set(self._h, idx, flat.ctypes.data_as(ctypes.c_void_p), 0))
+        elif a.shape == shape + (self.batch,):
+            flat = np.ascontiguousarray(a.reshape((n, self.batch), order="F").T)
+            _check(self._lib.tc_set(self._h, idx, flat.ctypes.data_as(ctypes.c_void_p), n))
+        else:
+            raise TenscalcError(f"set{key}: expected shape {shape} or {shape + (self.batch,)}, got {a.shape}")
+
+    def set_packed(self, key: str, packed: np.ndarray) -> None:
+        """values already laid out as C-contiguous [batch, n] (pinned host memory in bench.py)"""
+        idx = self._set_index[key]
+        _check(self._lib.tc_set(self._h, idx, packed.ctypes.data_as(ctypes.c_void_p), packed.shape[1]))
+
+    def solve(self, mu0: float = 1.0, maxIter: int = 200, saveIter: int = -1,
+              addEye2Hessian: Sequence[float] = (1e-9, 1e-9)):
+        """returns (status[batch] int32, iter[batch] int32, time in seconds for the batch)"""
+        mu = ctypes.c_double(mu0)
+        mi = ctypes.c_int32(maxIter)
+        si = ctypes.c_int32(saveIter)
+        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        status = np.empty(self.batch, dtype=np.int32)
+        it = np.empty(self.batch, dtype=np.int32)
+        t = ctypes.c_double(0)
+        _check(self._lib.tc_solve(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
+                                  status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p),
+                                  ctypes.byref(t)))
+        return status, it, t.value
+
+    def getOutputs(self) -> Union[List[np.ndarray], Dict[str, np.ndarray]]:
+        bufs = [np.empty((self.batch, int(np.prod(s)) if s else 1)) for _, s in self.gen.outputs]
+        ptrs = (ctypes.c_void_p * len(bufs))(*[b.ctypes.data_as(ctypes.c_void_p) for b in bufs])
+        _check(self._lib.tc_get_outputs(self._h, ptrs))
+        outs = [b.T.reshape(tuple(s) + (self.batch,), order="F") for b, (_, s) in zip(bufs, self.gen.outputs)]
+        if self.gen.output_is_struct:
+            return {n: o for (n, _), o in zip(self.gen.outputs, outs)}
+        return outs
+
+    # -- measurement hooks -------------------------------------------------------------------------
+    def last_solve_ms(self) -> float:
+        ms = ctypes.c_float(0)
+        _check(self._lib.tc_last_solve_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def kernel_launches(self) -> int:
+        c = ctypes.c_int64(0)
+        _check(self._lib.tc_kernel_launches(self._h, ctypes.byref(c)))
+        return c.value
+
+    def total_newton_steps(self) -> int:
+        c = ctypes.c_int64(0)
+        _check(self._lib.tc_total_newton_steps(self._h, ctypes.byref(c)))
+        return c.value
+
+    def scratch_bytes(self) -> int:
+        return int(self._lib.tc_scratch_bytes(self._h))
+
+    def synchronize(self) -> None:
+        _check(self._lib.tc_synchronize(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.tc_destroy(self._h)
+            self._h = None
+
+    delete = close
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
