@@ -77,6 +77,11 @@ void *tc_stream(tc_solver *s);                 /* cudaStream_t of the handle */
 int tc_last_solve_ms(tc_solver *s, float *ms); /* CUDA-event time of the last solve kernel */
 int tc_kernel_launches(const tc_solver *s, int64_t *count);
 int tc_total_newton_steps(tc_solver *s, int64_t *steps); /* sum of iter over the batch */
+/* Profiling counters, the batched form of the reference's `profiling` option
+ * (lib/@csparse/writeCfunctionpergroup.m:149-177): counts[g] = number of instance-executions
+ * of dependency group g since creation / the last reset.  counts has tc_num_groups entries. */
+int tc_num_groups(const tc_solver *s);
+int tc_group_counts(tc_solver *s, int64_t *counts, int reset);
 const char *tc_error_string(int code);
 
 #ifdef __cplusplus

@@ -31,17 +31,11 @@ OUT = os.path.join(HERE, "_ref")
 
 
 def pack_inputs(gen: GeneratedSolver, P: Dict[str, np.ndarray], V: Dict[str, np.ndarray], batch: int):
-    """[batch, n] C-contiguous blocks; every value array has the batch as LAST dimension
-    and is flattened column-major per instance (MATLAB layout)."""
-    def pack(spec, vals):
-        cols = []
-        for name, shape in spec:
-            a = np.asarray(vals[name], dtype=np.float64)
-            n = int(np.prod(shape)) if shape else 1
-            a = np.broadcast_to(a, tuple(shape) + (batch,)) if a.shape != tuple(shape) + (batch,) else a
-            cols.append(a.reshape((n, batch), order="F").T)
-        return np.ascontiguousarray(np.concatenate(cols, axis=1)) if cols else np.zeros((batch, 0))
-    return pack(gen.parameters, P), pack(gen.variables, V)
+    """[batch, nP] and [batch, nV] C-contiguous blocks (all set functions concatenated)"""
+    from tenscalc_b200.runtime import pack_inputs as pack_sets
+    Ps, Vs = pack_sets(gen, P, V, batch)
+    cat = lambda d: np.ascontiguousarray(np.concatenate(list(d.values()), axis=1)) if d else np.zeros((batch, 0))
+    return cat(Ps), cat(Vs)
 
 
 def unpack_outputs(gen: GeneratedSolver, Y: np.ndarray):

@@ -52,6 +52,7 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     const uint32_t *io;
     double *m;              // scratchbook, [n_slots][stride], instance-interleaved
     uint64_t *group_status; // [2][stride] lazy-evaluation flags per instance
+    unsigned long long *group_count; // [n_groups] instance-executions of every group (profiling)
     int64_t stride;         // padded batch (multiple of 32)
     int64_t batch;
     int32_t n_groups;

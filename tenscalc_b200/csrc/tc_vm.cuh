@@ -262,7 +262,13 @@ __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image
             int b = __ffsll((long long)bits) - 1;
             bits &= bits - 1;
             bool need = pred && !((c.st[w] >> b) & 1ull);
-            if (__any_sync(TC_FULL, need)) tc_exec_group(c, P.group_start, 64 * w + b, need);
+            const unsigned vote = __ballot_sync(TC_FULL, need);
+            if (vote) {
+                tc_exec_group(c, P.group_start, 64 * w + b, need);
+                // static per-group flop/byte tables x these counts = algorithmic work (the
+                // reference's profiling counters, writeCfunctionpergroup.m:149-177,481-492)
+                if (c.lane == 0) atomicAdd(P.group_count + 64 * w + b, (unsigned long long)__popc(vote));
+            }
             if (need) c.st[w] |= 1ull << b;
         }
     }

@@ -47,6 +47,8 @@ ABI = [
     ("tc_last_solve_ms", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     ("tc_kernel_launches", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     ("tc_total_newton_steps", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    ("tc_num_groups", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_group_counts", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     ("tc_error_string", ctypes.c_char_p, [ctypes.c_int]),
 ]
 
@@ -68,6 +70,31 @@ def load_library():
 
 class TenscalcError(RuntimeError):
     pass
+
+
+def pack_inputs(gen: GeneratedSolver, P: Dict[str, np.ndarray], V: Dict[str, np.ndarray], batch: int):
+    """Host layout of the C ABI: per set function one C-contiguous ``double[batch][n]`` block.
+    Value arrays carry the batch as LAST dimension (or none: broadcast) and are flattened
+    column-major per instance (MATLAB layout).  Returns ({name: block}, {name: block})."""
+    def pack(spec, vals):
+        out = {}
+        for name, shape in spec:
+            a = np.asarray(vals[name], dtype=np.float64)
+            n = int(np.prod(shape)) if shape else 1
+            if a.shape != tuple(shape) + (batch,):
+                a = np.broadcast_to(a.reshape(tuple(shape) + (1,)) if a.shape == tuple(shape) else a,
+                                    tuple(shape) + (batch,))
+            out[name] = np.ascontiguousarray(a.reshape((n, batch), order="F").T)
+        return out
+    return pack(gen.parameters, P), pack(gen.variables, V)
+
+
+def unpack_outputs(gen: GeneratedSolver, blocks: Sequence[np.ndarray]) -> Dict[str, np.ndarray]:
+    """inverse of the output layout: double[batch][n_k] blocks -> arrays shaped (..., batch)"""
+    outs = {}
+    for (name, shape), b in zip(gen.outputs, blocks):
+        outs[name] = b.T.reshape(tuple(shape) + (b.shape[0],), order="F")
+    return outs
 
 
 def _check(rc: int) -> None:
@@ -156,6 +183,53 @@ class BatchedSolver:
         if self.gen.output_is_struct:
             return {n: o for (n, _), o in zip(self.gen.outputs, outs)}
         return outs
+
+    # -- zero-copy variants (device pointers / caller-owned pinned buffers) ------------------------
+    def set_index(self, key: str) -> int:
+        """index of 'P_<name>' / 'V_<name>' in the C ABI's set table"""
+        return self._set_index[key]
+
+    def set_device_ptr(self, key: str, ptr: int, n: int) -> None:
+        """values are double[batch][n] in device memory at address `ptr`"""
+        _check(self._lib.tc_set_device(self._h, self._set_index[key], ctypes.c_void_p(ptr), n))
+
+    def solve_device_ptr(self, status_ptr: int, iter_ptr: int, mu0: float = 1.0, maxIter: int = 200,
+                         saveIter: int = -1, addEye2Hessian: Sequence[float] = (1e-9, 1e-9)) -> None:
+        """asynchronous solve; status/iter (int32[batch]) stay in device memory"""
+        mu = ctypes.c_double(mu0)
+        mi = ctypes.c_int32(maxIter)
+        si = ctypes.c_int32(saveIter)
+        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        _check(self._lib.tc_solve_device(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
+                                         ctypes.c_void_p(status_ptr), ctypes.c_void_p(iter_ptr)))
+
+    def solve_into(self, status: np.ndarray, it: np.ndarray, mu0: float = 1.0, maxIter: int = 200,
+                   saveIter: int = -1, addEye2Hessian: Sequence[float] = (1e-9, 1e-9)) -> float:
+        """`solve` writing status/iter into caller-owned (e.g. pinned) int32 host arrays"""
+        mu = ctypes.c_double(mu0)
+        mi = ctypes.c_int32(maxIter)
+        si = ctypes.c_int32(saveIter)
+        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        t = ctypes.c_double(0)
+        _check(self._lib.tc_solve(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
+                                  status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p),
+                                  ctypes.byref(t)))
+        return t.value
+
+    def get_outputs_ptrs(self, ptrs: Sequence[int], device: bool) -> None:
+        """getOutputs into caller-owned buffers, one double[batch][n_k] per output"""
+        arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
+        fn = self._lib.tc_get_outputs_device if device else self._lib.tc_get_outputs
+        _check(fn(self._h, arr))
+
+    def stream_ptr(self) -> int:
+        return int(self._lib.tc_stream(self._h) or 0)
+
+    def group_counts(self, reset: bool = False) -> np.ndarray:
+        n = self._lib.tc_num_groups(self._h)
+        c = np.zeros(n, dtype=np.int64)
+        _check(self._lib.tc_group_counts(self._h, c.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), int(reset)))
+        return c
 
     # -- measurement hooks -------------------------------------------------------------------------
     def last_solve_ms(self) -> float:

@@ -1,0 +1,204 @@
+"""Host-side generator logic (CPU only): symbolic derivatives, fixed-pattern LDL and solves,
+dependency groups / lazy re-evaluation, tape lowering.  Patterns follow the reference's
+examples/testing scripts: differential tests with seeded inputs and tolerance 1e3*eps
+(testLinearAlgebra.m:57-59, testFactorizations.m:46-91, testLDL.m:85-93, numericalGradient.m)."""
+import numpy as np
+import pytest
+
+from conftest import generated
+from tenscalc_b200 import itable as it
+from tenscalc_b200 import ldl as ldlmod
+from tenscalc_b200 import tensor as T
+from tenscalc_b200.differentiate import gradient, hessian
+from oracle.pyeval import evaluate
+
+EPS = np.finfo(float).eps
+
+
+def _vals(var, arr):
+    return dict(zip(var.flat(), np.asarray(arr, float).reshape(-1, order="F")))
+
+
+def test_hash_consing_and_normalisation():
+    T.clear()
+    tab = T.table()
+    a, b = T.Tvariable("a", 3), T.Tvariable("b", 3)
+    e1 = (a * b + b * a).flat()
+    e2 = (b * a + a * b).flat()
+    assert e1 == e2                                   # operands sorted, duplicates merged
+    assert (a - a).flat() == [None] * 3               # x-x is a structural zero
+    n = len(tab)
+    _ = a * b
+    assert len(tab) == n                              # appendUniqueInstruction: nothing new
+    assert T.Tvariable("c", 2).flat() != T.Tvariable("c", 2).flat()   # I_set never merged
+
+
+def test_gradient_and_hessian_against_finite_differences():
+    T.clear()
+    tab = T.table()
+    x = T.Tvariable("x", 4)
+    p = T.Tvariable("p", 4)
+    f = (T.norm2(x * p) + T.tsum(T.sqrt(x * x + 1.0), 0) + T.tsum(T.exp(x) / (p + 2.0), 0)
+         + T.tsum(T.sin(x) * T.cos(p), 0) + (x[0] * x[1] * x[2]) + T.tsum(T.atan(x), 0) + T.tsum(T.log(x * x + 2.0), 0))
+    u = x.flat()
+    H, g = hessian(tab, f.e[()], u)
+    rng = np.random.default_rng(0)
+    x0, p0 = rng.normal(size=4), rng.uniform(.5, 1.5, size=4)
+
+    def fval(xv):
+        return evaluate(tab, [f.e[()]], {**_vals(x, xv), **_vals(p, p0)})[0][0]
+
+    gv = np.array([evaluate(tab, [gi], {**_vals(x, x0), **_vals(p, p0)})[0][0] for gi in g])
+    h = 1e-6
+    gn = np.array([(fval(x0 + h * e) - fval(x0 - h * e)) / (2 * h) for e in np.eye(4)])
+    assert np.abs(gv - gn).max() <= 1e-7 * max(1, np.abs(gn).max())
+    Hv = np.zeros((4, 4))
+    for i in range(4):
+        for j, e in H[i].items():
+            Hv[i, j] = evaluate(tab, [e], {**_vals(x, x0), **_vals(p, p0)})[0][0]
+
+    def gval(xv):
+        return np.array([evaluate(tab, [gi], {**_vals(x, xv), **_vals(p, p0)})[0][0] for gi in g])
+    Hn = np.array([(gval(x0 + h * e) - gval(x0 - h * e)) / (2 * h) for e in np.eye(4)])
+    assert np.abs(Hv - Hn).max() <= 1e-6 * max(1, np.abs(Hn).max())
+    assert np.abs(Hv - Hv.T).max() <= 1e3 * EPS * np.abs(Hv).max()
+
+
+@pytest.mark.parametrize("n,density,seed", [(5, .75, 0), (6, .75, 1), (12, .3, 2), (20, .2, 3)])
+def test_ldl_identity_and_solve(n, density, seed):
+    """testFactorizations.m:46-91 (L*D*L'=A on random 75%-dense matrices) and testLDL.m
+    (ldl(A)\\B vs A\\B for n=6, m=2), tolerance 1e3*eps relative"""
+    rng = np.random.default_rng(seed)
+    M = rng.normal(size=(n, n)) * (rng.random((n, n)) < density)
+    A0 = M + M.T + np.diag(rng.uniform(2, 3, n) * np.where(np.arange(n) % 2, -1, 1) * n)   # quasi-definite-like
+    T.clear()
+    tab = T.table()
+    Av = T.Tvariable("A", [n, n])
+    rows = [{j: Av.e[i, j] for j in range(n) if A0[i, j] != 0} for i in range(n)]
+    fac = ldlmod.ldl(tab, rows)
+    vals = _vals(Av, np.tril(A0) + np.tril(A0, -1).T)
+    L = np.eye(n)
+    D = np.zeros(n)
+    for r in range(n):
+        for c, e in fac.L[r].items():
+            L[r, c] = evaluate(tab, [e], vals)[0][0]
+        D[r] = evaluate(tab, [fac.D[r]], vals)[0][0]
+    Pm = np.eye(n)[fac.p]                                  # permuted = P A P'
+    assert np.abs(L @ np.diag(D) @ L.T - Pm @ A0 @ Pm.T).max() <= 1e3 * EPS * np.abs(A0).max() * n
+    for m in range(2):
+        bv = T.Tvariable(f"b{m}", n)
+        b0 = rng.normal(size=n)
+        xs = ldlmod.solve(tab, fac, bv.flat())
+        xv = np.array([v[0] for v in evaluate(tab, xs, {**vals, **_vals(bv, b0)})])
+        xref = np.linalg.solve(A0, b0)
+        assert np.abs(xv - xref).max() <= 1e4 * EPS * np.linalg.cond(A0) * max(1, np.abs(xref).max())
+
+
+def test_ldl_structural_zero_pivot_is_an_error():
+    """sparsity_ldl.m:187-189: "ldl needs pivoting" is a generation-time error"""
+    T.clear()
+    tab = T.table()
+    a = T.Tvariable("a", 1).flat()[0]
+    with pytest.raises(ValueError):
+        ldlmod.ldl(tab, [{1: a}, {0: a}], order=[0, 1])
+
+
+def test_minimum_degree_ordering_is_a_permutation_and_reduces_fill():
+    gen, _ = generated("mpc_dcmotor")
+    assert gen.info["kkt"] == 323
+    assert gen.info["nnzL"] < 323 * 6, "banded MPC KKT must factor with O(n) fill"
+
+
+def test_dependency_groups_lazy_semantics():
+    """a set invalidates exactly the groups that depend on it; a get runs exactly its stale
+    parents, in topological order (writeCfunctionpergroup.m:566-571,653-657)"""
+    gen, _ = generated("sls")
+    pr = gen.problem
+    tab = pr.tab
+    for g, members in enumerate(pr.groups):          # groups are topologically ordered
+        for i in members:
+            for o in tab.operands[i]:
+                go = pr.group_of.get(o)
+                assert go is None or go <= g
+    mu_children = set(pr.sets["setMu__"].children)
+    ap_children = set(pr.sets["setAlphaPrimal__"].children)
+    par_children = set(pr.sets["setP_A"].children)
+    grad_parents = set(pr.gets["getNorminf_Grad__"].parents)
+    minF_parents = set(pr.gets["getMinF_s__"].parents)
+    assert not (mu_children & grad_parents), "the gradient of the Lagrangian does not depend on mu"
+    assert ap_children & minF_parents, "the line-search value depends on alphaPrimal"
+    assert ap_children <= set(pr.copies["updatePrimalDual__"].parents) | minF_parents
+    # parameter-only groups (A'A-like subexpressions) are not invalidated by the primal update
+    upd_children = set(pr.copies["updatePrimalDual__"].children)
+    assert par_children - upd_children, "parameter-only groups must exist (evaluated once per setP_*)"
+
+
+def test_memory_map_never_aliases_live_values():
+    gen, _ = generated("mpc_dcmotor")
+    pr = gen.problem
+    tab, slot = pr.tab, pr.slot
+    owner = {}
+    pinned = set()
+    for g in pr.gets.values():
+        pinned.update(x for s in g.sources for x in s if x is not None)
+    for c in pr.copies.values():
+        pinned.update(c.src)
+    for members in pr.groups:
+        for i in members:
+            for o in tab.operands[i]:
+                if tab.types[o] in (it.I_load, it.I_2) and slot[o] < 0:
+                    continue
+                assert owner.get(int(slot[o]), o) == o, "operand slot was overwritten before its last use"
+            assert all(slot[i] != slot[o] for o in tab.operands[i]), "result aliases an operand"
+            owner[int(slot[i])] = i
+    for i in pinned:
+        assert owner.get(int(slot[i]), i) == i or tab.types[i] == it.I_set
+
+
+def test_tape_decodes_back_to_the_instruction_list():
+    from tenscalc_b200 import tape
+    gen, _ = generated("sls")
+    pr = gen.problem
+    L = tape.lower(gen)
+    words = L["tape"]
+    pc = 0
+    for g, members in enumerate(pr.groups):
+        assert pc == L["group_start"][g]
+        for i in members:
+            hdr, r = int(words[pc]), int(words[pc + 1])
+            op, n = hdr & 0xFF, hdr >> 8
+            pc += 2
+            t = pr.tab.types[i]
+            if t in (it.I_load, it.I_2):
+                assert op == it.I_sum and n == 1 and words[pc] & tape.CONST_BIT
+            else:
+                assert op == t and n == len(pr.tab.operands[i]) and r == pr.slot[i]
+                if t == it.I_sumprod:
+                    assert words[pc] == int(pr.tab.params[i][0])
+                    pc += 1
+                for k, o in enumerate(pr.tab.operands[i]):
+                    w = int(words[pc + k])
+                    if not w & tape.CONST_BIT:
+                        assert (w & 0x3FFFFFFF) == pr.slot[o]
+            pc += n
+    assert pc == len(words) == L["group_start"][-1]
+
+
+def test_reference_rejected_options_raise():
+    """ipmPD_CStimesLambda.m:31-48 raises for these; so does the generator here"""
+    from tenscalc_b200.optimize import cmex2optimizeCS
+    T.clear()
+    x = T.Tvariable("x", 2)
+    for kw in (dict(smallerNewtonMatrix=True), dict(useLDL=False), dict(useUmfpack=True)):
+        with pytest.raises(NotImplementedError):
+            cmex2optimizeCS(classname="t", objective=T.norm2(x), optimizationVariables=[x], **kw)
+    with pytest.raises(ValueError):
+        cmex2optimizeCS(classname="t", objective=x, optimizationVariables=[x])
+
+
+def test_problem_sizes_match_survey_table():
+    sizes = dict(sls=(8, 0, 16), mpc_dcmotor=(89, 60, 174), l1l2=(996, 0, 796), mpc_quadcopter=(700, 406, 300))
+    for name, (nU, nG, nF) in sizes.items():
+        gen, _ = generated(name)
+        d = gen.defines
+        assert (d["nU"], d["nG"], d["nF"]) == (nU, nG, nF), name
