@@ -54,9 +54,9 @@ class Oracle:
         self.kind = kind
         os.makedirs(OUT, exist_ok=True)
         if tag is None:
-            # the library is tied to the exact instruction list: key it by the device image
-            from tenscalc_b200 import tape
-            tag = gen.classname + "_" + hashlib.sha1(tape.serialize(gen)).hexdigest()[:10]
+            # the library is tied to the exact instruction list (not to the device tape format)
+            from tenscalc_b200.csparse import fingerprint
+            tag = gen.classname + "_" + fingerprint(gen.problem)[:10]
         self.opt = opt
         self.so = os.path.join(OUT, f"{tag}_{kind}{opt.replace('-', '_')}.so")
         self.lib = None

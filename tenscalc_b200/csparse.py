@@ -67,6 +67,24 @@ class CompiledProblem:
     flops_per_group: List[int] = field(default_factory=list)
 
 
+def fingerprint(pr: CompiledProblem) -> str:
+    """hash of the exact instruction list, memory map, groups and #define table: two problems
+    with the same fingerprint compile to the same straight-line code on every back end"""
+    import hashlib
+    h = hashlib.sha1()
+    tab = pr.tab
+    for members in pr.groups:
+        h.update(np.asarray(members, dtype=np.int64).tobytes())
+        for i in members:
+            h.update(repr((tab.types[i], tab.params[i], tab.operands[i])).encode())
+    h.update(np.asarray(pr.slot, dtype=np.int64).tobytes())
+    h.update(repr(sorted(pr.defines.items())).encode())
+    for d in (pr.sets, pr.gets, pr.copies):
+        for k, v in d.items():
+            h.update(repr((k, getattr(v, "dest", None), getattr(v, "src", None), getattr(v, "sources", None))).encode())
+    return h.hexdigest()
+
+
 class CSparse:
     def __init__(self, tab: InstructionTable):
         self.tab = tab

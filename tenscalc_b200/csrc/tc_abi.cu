@@ -9,14 +9,13 @@
 #include "../../include/tenscalc_b200.h"
 #include "tc_driver.cuh"
 
-#define TC_BLOCK 128   // threads per CTA = instances per CTA; the stride is a multiple of it
-
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &P, int64_t inst) {
-    c.mb = P.m + inst;
-    c.stride = P.stride;
+    __shared__ double ring[TC_RING * TC_BLOCK];     // result ring, [slot][thread]: conflict-free
+    c.ring = ring + threadIdx.x;
+    c.mb = &TC_M(P, 0, inst);
     c.consts = P.consts;
     c.tape = P.tape;
     c.lane = threadIdx.x & 31u;
@@ -30,7 +29,7 @@ __device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device
 }
 
 // whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
-__global__ void __launch_bounds__(TC_BLOCK) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
+__global__ void __launch_bounds__(TC_BLOCK, 3) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
                                                             double aeU, double aeEq,
                                                             int32_t *__restrict__ status,
                                                             int32_t *__restrict__ iter) {
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(TC_BLOCK) tc_solve_kernel(tc_device_image P, d
 }
 
 // lazy evaluation of the parents of one get function (classname_getOutputs)
-__global__ void __launch_bounds__(TC_BLOCK) tc_eval_kernel(tc_device_image P, int fn) {
+__global__ void __launch_bounds__(TC_BLOCK, 3) tc_eval_kernel(tc_device_image P, int fn) {
     const int64_t inst = (int64_t)blockIdx.x * TC_BLOCK + threadIdx.x;
     tc_lane c;
     tc_lane_init(c, P, inst);
@@ -74,7 +73,7 @@ __global__ void tc_set_kernel(tc_device_image P, int fn, const double *__restric
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // rows = entries, cols = instances
         uint32_t k = k0 + j;
         int64_t b = b0 + threadIdx.x;
-        if (b < P.batch && k < n) P.m[(size_t)P.io[f.io_off + k] * P.stride + b] = tile[threadIdx.x][j];
+        if (b < P.batch && k < n) TC_M(P, P.io[f.io_off + k], b) = tile[threadIdx.x][j];
     }
     if (blockIdx.y == 0 && threadIdx.y == 0) {
         int64_t b = b0 + threadIdx.x;
@@ -97,7 +96,7 @@ __global__ void tc_gather_kernel(tc_device_image P, uint32_t io_off, uint32_t n,
             uint32_t w = P.io[io_off + k];
             double v = 0.0;
             if (w != TC_NO_SLOT)
-                v = (w & TC_CONST_BIT) ? P.consts[w & TC_SLOT_MASK] : P.m[(size_t)(w & TC_SLOT_MASK) * P.stride + b];
+                v = (w & TC_CONST_BIT) ? P.consts[w & TC_SLOT_MASK] : TC_M(P, w & TC_SLOT_MASK, b);
             tile[j][threadIdx.x] = v;
         }
     }
@@ -185,18 +184,22 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     s->batch = batch;
     s->stride = (batch + TC_BLOCK - 1) / TC_BLOCK * TC_BLOCK;
     const int64_t n_slots = ih[1], n_groups = ih[2], n_funcs = ih[3], n_sets = ih[4], n_out = ih[5],
-                  tape_words = ih[6], n_consts = ih[7], io_words = ih[8];
+                  tape_cells = ih[6], n_consts = ih[7], io_words = ih[8];
     s->n_slots = n_slots;
-    auto pad8 = [](size_t b) { return (b + 7) / 8 * 8; };
+    auto pad16 = [](size_t b) { return (b + 15) / 16 * 16; };
     const char *p = (const char *)(dh + 16);
-    const uint32_t *group_start = (const uint32_t *)p; p += pad8((n_groups + 1) * 4);
-    const uint32_t *tape = (const uint32_t *)p;        p += pad8(tape_words * 4);
-    const double *consts = (const double *)p;          p += pad8(n_consts * 8);
-    const tc_func *funcs = (const tc_func *)p;         p += pad8(n_funcs * sizeof(tc_func));
-    const uint32_t *io = (const uint32_t *)p;          p += pad8(io_words * 4);
-    const uint32_t *set_fids = (const uint32_t *)p;    p += pad8(n_sets * 4);
-    const uint32_t *out_sizes = (const uint32_t *)p;   p += pad8(n_out * 4);
-    if ((size_t)(p - (const char *)image) > image_bytes || n_groups > 128) { delete s; return TC_EFORMAT; }
+    const uint32_t *group_start = (const uint32_t *)p; p += pad16((n_groups + 1) * 4);
+    const uint4 *tape = (const uint4 *)p;              p += pad16(tape_cells * sizeof(uint4));
+    const double *consts = (const double *)p;          p += pad16(n_consts * 8);
+    const tc_func *funcs = (const tc_func *)p;         p += pad16(n_funcs * sizeof(tc_func));
+    const uint32_t *io = (const uint32_t *)p;          p += pad16(io_words * 4);
+    const uint32_t *set_fids = (const uint32_t *)p;    p += pad16(n_sets * 4);
+    const uint32_t *out_sizes = (const uint32_t *)p;   p += pad16(n_out * 4);
+    if ((size_t)(p - (const char *)image) > image_bytes || n_groups > 128 || ih[9] != TC_RING ||
+        ih[10] != TC_BUNDLE || tape_cells % TC_BUNDLE) {
+        delete s;
+        return TC_EFORMAT;
+    }
 
     int rc = 0;
 #define TC_TRY(x) do { rc = (x); if (rc) { tc_destroy(s); return rc; } } while (0)
@@ -206,7 +209,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     TC_TRY((int)cudaEventCreate(&s->ev1));
     tc_device_image &I = s->img;
     TC_TRY(tc_upload(s, group_start, (n_groups + 1) * 4, 0, (const void **)&I.group_start));
-    TC_TRY(tc_upload(s, tape, tape_words * 4, 64 * 4, (const void **)&I.tape));   // reader prefetches a window
+    TC_TRY(tc_upload(s, tape, tape_cells * sizeof(uint4), 0, (const void **)&I.tape));
     TC_TRY(tc_upload(s, consts, n_consts * 8, 0, (const void **)&I.consts));
     TC_TRY(tc_upload(s, funcs, n_funcs * sizeof(tc_func), 0, (const void **)&I.funcs));
     TC_TRY(tc_upload(s, io, io_words * 4, 0, (const void **)&I.io));
@@ -230,6 +233,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     s->d_iter = s->d_status + s->stride;
     s->d_sum = (unsigned long long *)(s->d_iter + s->stride);
     I.stride = s->stride;
+    I.n_slots = n_slots;
     I.batch = batch;
     I.n_groups = (int32_t)n_groups;
     tc_defines &D = I.def;

@@ -2,12 +2,35 @@
 // Written by tenscalc_b200/tape.py (serialize); see that file for the tape encoding.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
-#define TC_MAGIC 0x3030324243540001LL
-#define TC_CONST_BIT 0x40000000u
-#define TC_NEG_BIT 0x80000000u
+#define TC_MAGIC 0x3030324243540002LL
+#define TC_CONST_BIT 0x40000000u   // io[] words (get/copy sources): constant-pool index
 #define TC_SLOT_MASK 0x3FFFFFFFu
 #define TC_NO_SLOT 0xFFFFFFFFu
+#define TC_BUNDLE 8                // cells fetched together        -- MUST match tape.py BUNDLE
+#define TC_RING 32                 // results in the per-lane ring  -- MUST match tape.py RING
+
+// tape cell = uint4 {op|flags|ring slot<<16, operand A, operand B, result slot}; see tape.py
+#define TC_SP_SLOT 0u
+#define TC_SP_CONST 1u
+#define TC_SP_RING 2u
+#define TC_SP_NONE 3u
+#define TC_F_STORE (1u << 8)
+#define TC_F_END (1u << 9)
+#define TC_F_NEG (1u << 10)
+#define TC_F_NEGA (1u << 11)
+#define TC_F_NEGB (1u << 12)
+#define TC_F_INIT (1u << 13)
+
+enum tc_cellop {   // MUST match the OP_* list of tenscalc_b200/tape.py
+    OP_NOP = 0, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2, OP_MSET, OP_MADD, OP_PSET, OP_PMUL1, OP_PMUL2,
+    OP_P1SET, OP_P1ADD, OP_P2SET, OP_P2ADD, OP_RSUB, OP_RSUBDIV, OP_NEGDIV, OP_DIV, OP_SQ1F, OP_SQ2F,
+    OP_SQ1, OP_SQ2, OP_ABS1F, OP_ABS2F, OP_ABS1, OP_ABS2, OP_MINF1, OP_MINF2, OP_MIN1, OP_MIN2,
+    OP_MAXF1, OP_MAXF2, OP_MAX1, OP_MAX2, OP_AMAXF1, OP_AMAXF2, OP_AMAX1, OP_AMAX2, OP_CLP, OP_PACC,
+    OP_UNARY = 64   // + reference opcode of the unary function
+};
+#define TC_TILE 32   // instances per scratchbook tile = lanes per warp
 
 // driver function ids -- MUST match FN in tenscalc_b200/tape.py.  Names are the reference's
 // (lib/ipmPD_CStimesLambda.m declares them, lib/ipmPD_CSsolver.c:28-51 calls them).
@@ -45,12 +68,16 @@ struct tc_defines {         // the #define table of lib/cmex2optimizeCS.m:303-33
 };
 
 struct tc_device_image {    // device pointers, passed by value to the kernels
-    const uint32_t *tape;
-    const uint32_t *group_start;
+    const uint4 *tape;            // cells
+    const uint32_t *group_start;  // first cell of every group (multiples of TC_BUNDLE)
     const double *consts;
     const tc_func *funcs;
     const uint32_t *io;
-    double *m;              // scratchbook, [n_slots][stride], instance-interleaved
+    double *m;              // scratchbook, [stride/32][n_slots][32]: 32 consecutive instances (one warp)
+                            // share one contiguous n_slots*256-byte block, lane-interleaved, so a warp-wide
+                            // operand access is one 256-byte segment and a warp's whole working set sits
+                            // in a handful of 2 MB pages (TLB reach) instead of being strided over the batch
+    int64_t n_slots;
     uint64_t *group_status; // [2][stride] lazy-evaluation flags per instance
     unsigned long long *group_count; // [n_groups] instance-executions of every group (profiling)
     int64_t stride;         // padded batch (multiple of 32)
@@ -58,3 +85,7 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     int32_t n_groups;
     tc_defines def;
 };
+
+// address of scratchbook slot `slot` of instance `inst`
+#define TC_M(P, slot, inst) \
+    ((P).m[((size_t)((inst) >> 5) * (size_t)(P).n_slots + (size_t)(slot)) * TC_TILE + ((inst) & 31)])

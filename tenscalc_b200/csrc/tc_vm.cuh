@@ -2,12 +2,21 @@
 //
 // Replaces the per-problem C functions `classname_groupK()` that the reference emits with
 // writeCinstructionsC (lib/csparse/instructionsTableUTHash.c:950-1539).  The 32 lanes of a
-// warp walk the SAME tape (so there is no divergence inside a group) and each lane applies
-// it to its own instance.  The scratchbook is instance-interleaved, m[slot][instance], so a
-// warp-wide operand load is one contiguous 256-byte segment.
+// warp walk the SAME tape (no divergence inside a group) and each lane applies it to its own
+// instance.  The scratchbook is tiled per warp and lane-interleaved (tc_image.h), so a
+// warp-wide operand access is one contiguous 256-byte segment.
 //
-// Arithmetic contract (parity with the CPU oracle): every instruction is evaluated in the
-// C expression order of the reference emitter, with separately rounded multiplies and adds
+// Execution model (tape format: tenscalc_b200/tape.py).  The tape is a sequence of 128-bit
+// cells of an accumulator machine (registers acc, p; up to two memory operands per cell).
+// Cells are processed in bundles of TC_BUNDLE: while bundle b executes, the 2*TC_BUNDLE
+// scratchbook/constant operands of bundle b+1 are already in flight (branch-free, predicated
+// loads issued back to back), which is what hides HBM latency at modest occupancy.  Operands
+// produced by one of the last TC_RING instructions never come from the scratchbook -- the
+// lowering routes them through the per-lane RESULT RING in shared memory -- so fetching a
+// bundle early can never read a stale value, and short-lived temporaries never touch HBM.
+//
+// Arithmetic contract (parity with the CPU oracle): every instruction is evaluated in the C
+// expression order of the reference emitter, with separately rounded multiplies and adds
 // (__dmul_rn/__dadd_rn are never contracted into DFMA), IEEE division and square root.
 #pragma once
 #include <cfloat>
@@ -17,89 +26,16 @@
 #include "tc_image.h"
 
 #define TC_FULL 0xFFFFFFFFu
-#define TC_CHUNK 8
+#define TC_BLOCK 128   // threads per CTA = instances per CTA; the batch stride is a multiple of it
 
 struct tc_lane {
-    double *mb;          // &m[0][instance]
-    int64_t stride;
+    double *mb;            // &m[tile][0][lane]; slot k of this instance is mb[k*32]
     const double *consts;
-    const uint32_t *tape;
+    const uint4 *tape;
+    double *ring;          // shared memory, &ring[0][thread]; result k lives at ring[k*TC_BLOCK]
     unsigned lane;
-    uint64_t st[2];      // groupStatus[] of this instance, one bit per group
+    uint64_t st[2];        // groupStatus[] of this instance, one bit per group
 };
-
-// The tape is fetched cooperatively: 32 consecutive words per warp load, then broadcast
-// word by word with a shuffle -- one LSU wavefront per 32 tape words instead of one per word.
-struct tc_tape_reader {
-    const uint32_t *base;
-    uint32_t pc, win;
-    unsigned lane;
-    __device__ __forceinline__ void seek(uint32_t p) {
-        pc = p;
-        win = __ldg(base + (p & ~31u) + lane);
-    }
-    __device__ __forceinline__ uint32_t next() {
-        uint32_t w = __shfl_sync(TC_FULL, win, pc & 31u);
-        pc++;
-        if ((pc & 31u) == 0) win = __ldg(base + pc + lane);
-        return w;
-    }
-};
-
-__device__ __forceinline__ double tc_ldop(const tc_lane &c, uint32_t w, bool pred) {
-    uint32_t idx = w & TC_SLOT_MASK;
-    double v;
-    if (w & TC_CONST_BIT) v = __ldg(c.consts + idx);                 // warp-uniform branch
-    else v = pred ? c.mb[(size_t)idx * (size_t)c.stride] : 0.0;
-    return (w & TC_NEG_BIT) ? -v : v;
-}
-
-template <int N>
-__device__ __forceinline__ void tc_load_chunk(const tc_lane &c, tc_tape_reader &tr, double (&v)[N], int cnt,
-                                              bool pred) {
-    uint32_t w[N];
-#pragma unroll
-    for (int j = 0; j < N; j++)
-        if (j < cnt) w[j] = tr.next();
-#pragma unroll
-    for (int j = 0; j < N; j++)
-        if (j < cnt) v[j] = tc_ldop(c, w[j], pred);
-}
-
-// sum_k x_{2k}*x_{2k+1}, left to right, over `npairs` pairs read from the tape
-__device__ __forceinline__ double tc_dot_pairs(const tc_lane &c, tc_tape_reader &tr, int npairs, bool pred) {
-    double acc = 0.0;
-    bool first = true;
-    for (int k = 0; k < npairs; k += TC_CHUNK / 2) {
-        int cnt = min(TC_CHUNK / 2, npairs - k);
-        double v[TC_CHUNK];
-        tc_load_chunk<TC_CHUNK>(c, tr, v, 2 * cnt, pred);
-#pragma unroll
-        for (int j = 0; j < TC_CHUNK / 2; j++)
-            if (j < cnt) {
-                double p = __dmul_rn(v[2 * j], v[2 * j + 1]);
-                acc = first ? p : __dadd_rn(acc, p);
-                first = false;
-            }
-    }
-    return acc;
-}
-
-template <int M>
-__device__ __forceinline__ double tc_sumprod_m(const tc_lane &c, tc_tape_reader &tr, int nprod, bool pred) {
-    double acc = 0.0;
-    bool first = true;
-    for (int k = 0; k < nprod; k++) {
-        double v[M];
-        tc_load_chunk<M>(c, tr, v, M, pred);
-        double p = v[0];
-#pragma unroll
-        for (int j = 1; j < M; j++) p = __dmul_rn(p, v[j]);
-        acc = first ? p : __dadd_rn(acc, p);
-        first = false;
-    }
-    return acc;
-}
 
 __device__ __forceinline__ double tc_unary(int op, double x) {
     switch (op) {   // C forms: instructionsTableUTHash.c:1347-1539
@@ -140,120 +76,142 @@ __device__ __forceinline__ double tc_unary(int op, double x) {
     return x;
 }
 
+// rare cell kinds, kept out of line so that the hot dispatch stays small
+__device__ __noinline__ double tc_cell_slow(unsigned op, unsigned w0, double acc, double x, double y) {
+    switch (op) {
+    case OP_SQ1F: return __dmul_rn(x, x);                              // a*a+b*b+...   :1201-1210
+    case OP_SQ2F: return __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    case OP_SQ1: return __dadd_rn(acc, __dmul_rn(x, x));
+    case OP_SQ2: return __dadd_rn(__dadd_rn(acc, __dmul_rn(x, x)), __dmul_rn(y, y));
+    case OP_ABS1F: return fabs(x);                                     // |a|+|b|+...   :1217-1225
+    case OP_ABS2F: return __dadd_rn(fabs(x), fabs(y));
+    case OP_ABS1: return __dadd_rn(acc, fabs(x));
+    case OP_ABS2: return __dadd_rn(__dadd_rn(acc, fabs(x)), fabs(y));
+    // sequential compare chains (:1228-1313): a NaN in a non-first operand is dropped
+    case OP_MINF1: return x;
+    case OP_MINF2: acc = x; if (acc > y) acc = y; return acc;
+    case OP_MIN2: if (w0 & TC_F_INIT) acc = 0.0; if (acc > x) acc = x; if (acc > y) acc = y; return acc;
+    case OP_MIN1: if (w0 & TC_F_INIT) acc = 0.0; if (acc > x) acc = x; return acc;
+    case OP_MAXF1: return x;
+    case OP_MAXF2: acc = x; if (acc < y) acc = y; return acc;
+    case OP_MAX2: if (w0 & TC_F_INIT) acc = 0.0; if (acc < x) acc = x; if (acc < y) acc = y; return acc;
+    case OP_MAX1: if (w0 & TC_F_INIT) acc = 0.0; if (acc < x) acc = x; return acc;
+    case OP_AMAXF1: return fabs(x);
+    case OP_AMAXF2: acc = fabs(x); if (acc < fabs(y)) acc = fabs(y); return acc;
+    case OP_AMAX2: if (acc < fabs(x)) acc = fabs(x); if (acc < fabs(y)) acc = fabs(y); return acc;
+    case OP_AMAX1: if (acc < fabs(x)) acc = fabs(x); return acc;
+    case OP_CLP:                                                       // :1315-1331
+        if (w0 & TC_F_INIT) acc = DBL_MAX;
+        if (y < 0) {
+            double q = (-x) / y;
+            if (acc > q) acc = q;
+        }
+        return acc;
+    case OP_DIV: return x / y;
+    case OP_NEGDIV: return (-acc) / x;                                 // -(dot)/d      :1106-1121
+    default: return tc_unary((int)op - OP_UNARY, x);
+    }
+}
+
+// Operand fetch, look-ahead part: scratchbook slots only, one predicated load each (no branch,
+// so the 2*TC_BUNDLE loads of a bundle issue back to back).  Constants (~1% of operands) and
+// ring operands are read at execution time.
+__device__ __forceinline__ double tc_fetch(const double *mb, unsigned w, bool pred) {
+    double v = 0.0;
+    if (pred && (w >> 30) == TC_SP_SLOT) v = mb[(size_t)w * TC_TILE];   // space 0: w == slot index
+    return v;
+}
+
+// execution-time operands: result ring (shared memory) or constant pool; warp-uniform branches
+__device__ __forceinline__ double tc_late(const tc_lane &c, const double *ring, unsigned w, double v) {
+    const unsigned sp = w >> 30;
+    if (sp == TC_SP_RING) v = ring[(w & 0xffu) * TC_BLOCK];
+    else if (sp == TC_SP_CONST) v = __ldg(c.consts + (w & TC_SLOT_MASK));
+    return v;
+}
+
 // Execute dependency group g for the lanes with pred set.  Must be called by all 32 lanes.
 __device__ __noinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_start, int g, bool pred) {
-    tc_tape_reader tr;
-    tr.base = c.tape;
-    tr.lane = c.lane;
-    tr.seek(__ldg(group_start + g));
-    const uint32_t end = __ldg(group_start + g + 1);
-    while (tr.pc < end) {
-        const uint32_t hdr = tr.next();
-        const int op = hdr & 0xff;
-        int n = hdr >> 8;
-        const uint32_t r = tr.next();
-        double acc = 0.0;
-        switch (op) {
-        case I_sum: {                                       // +a-b+c...       :964-968
-            bool first = true;
-            for (int k = 0; k < n; k += TC_CHUNK) {
-                int cnt = min(TC_CHUNK, n - k);
-                double v[TC_CHUNK];
-                tc_load_chunk<TC_CHUNK>(c, tr, v, cnt, pred);
+    const uint4 *cells = c.tape + __ldg(group_start + g);
+    const int nb = (int)((__ldg(group_start + g + 1) - __ldg(group_start + g)) / TC_BUNDLE);
+    double *const mb = c.mb;
+    double *const ring = c.ring;
+    double acc = 0.0, p = 0.0;
+
+    uint4 cn[TC_BUNDLE];          // next bundle: cells and operand values in flight
+    double xn[TC_BUNDLE], yn[TC_BUNDLE];
 #pragma unroll
-                for (int j = 0; j < TC_CHUNK; j++)
-                    if (j < cnt) {
-                        acc = first ? v[j] : __dadd_rn(acc, v[j]);
-                        first = false;
-                    }
-            }
-        } break;
-        case I_sumprod: {                                   // a*b+c*d+...     :1007-1029
-            const int m = (int)tr.next();
-            if (m == 2) acc = tc_dot_pairs(c, tr, n / 2, pred);
-            else if (m == 3) acc = tc_sumprod_m<3>(c, tr, n / 3, pred);
-            else if (m == 4) acc = tc_sumprod_m<4>(c, tr, n / 4, pred);
-            else {
-                bool first = true;
-                for (int k = 0; k < n; k += m) {
-                    double p = tc_ldop(c, tr.next(), pred);
-                    for (int j = 1; j < m; j++) p = __dmul_rn(p, tc_ldop(c, tr.next(), pred));
-                    acc = first ? p : __dadd_rn(acc, p);
-                    first = false;
-                }
-            }
-        } break;
-        case I_plus_minus_dot_div: {                        // (a0-(..))/d     :1081-1098
-            double a0 = tc_ldop(c, tr.next(), pred);
-            double d = tc_ldop(c, tr.next(), pred);
-            acc = __dadd_rn(a0, -tc_dot_pairs(c, tr, (n - 2) / 2, pred)) / d;
-        } break;
-        case I_minus_dot_div: {                             // -(..)/d         :1106-1121
-            double d = tc_ldop(c, tr.next(), pred);
-            acc = (-tc_dot_pairs(c, tr, (n - 1) / 2, pred)) / d;
-        } break;
-        case I_plus_minus_dot: {                            // a0-(..)         :1128-1144
-            double a0 = tc_ldop(c, tr.next(), pred);
-            acc = __dadd_rn(a0, -tc_dot_pairs(c, tr, (n - 1) / 2, pred));
-        } break;
-        case I_minus_dot:                                   // -(..)           :1151-1164
-            acc = -tc_dot_pairs(c, tr, n / 2, pred);
-            break;
-        case I_div: {
-            double a = tc_ldop(c, tr.next(), pred);
-            double b = tc_ldop(c, tr.next(), pred);
-            acc = a / b;
-        } break;
-        case I_plus_sqr:                                    // a*a+b*b+...     :1201-1210
-        case I_plus_abs:                                    // |a|+|b|+...     :1217-1225
-        case I_min:
-        case I_max:
-        case I_min0:
-        case I_max0:
-        case I_max_abs: {                                   // sequential compare chains :1228-1313
-            bool first = !(op == I_min0 || op == I_max0);   // the ...0 forms start from 0
-            for (int k = 0; k < n; k += TC_CHUNK) {
-                int cnt = min(TC_CHUNK, n - k);
-                double v[TC_CHUNK];
-                tc_load_chunk<TC_CHUNK>(c, tr, v, cnt, pred);
+    for (int j = 0; j < TC_BUNDLE; j++) cn[j] = __ldg(cells + j);
 #pragma unroll
-                for (int j = 0; j < TC_CHUNK; j++)
-                    if (j < cnt) {
-                        double x = v[j];
-                        if (op == I_plus_sqr) x = __dmul_rn(x, x);
-                        else if (op == I_plus_abs || op == I_max_abs) x = fabs(x);
-                        if (first) acc = x;
-                        else if (op == I_plus_sqr || op == I_plus_abs) acc = __dadd_rn(acc, x);
-                        else if (op == I_min || op == I_min0) { if (acc > x) acc = x; }
-                        else { if (acc < x) acc = x; }      // NaN in a non-first operand is dropped
-                        first = false;
-                    }
-            }
-        } break;
-        case I_clp: {                                       // :1315-1331
-            acc = DBL_MAX;
-            for (int k = 0; k < n; k += TC_CHUNK) {
-                int cnt = min(TC_CHUNK, n - k);
-                double v[TC_CHUNK];
-                tc_load_chunk<TC_CHUNK>(c, tr, v, cnt, pred);
+    for (int j = 0; j < TC_BUNDLE; j++) {
+        xn[j] = tc_fetch(mb, cn[j].y, pred);
+        yn[j] = tc_fetch(mb, cn[j].z, pred);
+    }
+    for (int b = 0; b < nb; b++) {
+        uint4 cc[TC_BUNDLE];
+        double xc[TC_BUNDLE], yc[TC_BUNDLE];
 #pragma unroll
-                for (int j = 0; j < TC_CHUNK; j += 2)
-                    if (j < cnt) {
-                        if (v[j + 1] < 0) {
-                            double x = (-v[j]) / v[j + 1];
-                            if (acc > x) acc = x;
-                        }
-                    }
-            }
-        } break;
-        default:
-            acc = tc_unary(op, tc_ldop(c, tr.next(), pred));
+        for (int j = 0; j < TC_BUNDLE; j++) {
+            cc[j] = cn[j];
+            xc[j] = xn[j];
+            yc[j] = yn[j];
         }
-        if (pred) c.mb[(size_t)r * (size_t)c.stride] = acc;
+        if (b + 1 < nb) {         // warp-uniform: put the next bundle in flight before executing this one
+            const uint4 *nx = cells + (size_t)(b + 1) * TC_BUNDLE;
+#pragma unroll
+            for (int j = 0; j < TC_BUNDLE; j++) cn[j] = __ldg(nx + j);
+#pragma unroll
+            for (int j = 0; j < TC_BUNDLE; j++) {
+                xn[j] = tc_fetch(mb, cn[j].y, pred);
+                yn[j] = tc_fetch(mb, cn[j].z, pred);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TC_BUNDLE; j++) {
+            const unsigned w0 = cc[j].x;
+            const unsigned op = w0 & 0xffu;
+            const double x = tc_late(c, ring, cc[j].y, xc[j]);
+            const double y = tc_late(c, ring, cc[j].z, yc[j]);
+            switch (op) {
+            case OP_NOP: break;
+            case OP_MADD: acc = __dadd_rn(acc, __dmul_rn(x, y)); break;            // a*b+c*d+...  :1007-1029
+            case OP_MSET: acc = __dmul_rn(x, y); break;
+            case OP_RSUBDIV: acc = __dadd_rn(x, -acc) / y; break;                  // (a0-(dot))/d :1081-1098
+            case OP_RSUB: acc = __dadd_rn(x, -acc); break;                         // a0-(dot)     :1128-1144
+            case OP_SUM2F:                                                         // +a-b+c...    :964-968
+                acc = __dadd_rn((w0 & TC_F_NEGA) ? -x : x, (w0 & TC_F_NEGB) ? -y : y);
+                break;
+            case OP_SUM2:
+                acc = __dadd_rn(__dadd_rn(acc, (w0 & TC_F_NEGA) ? -x : x), (w0 & TC_F_NEGB) ? -y : y);
+                break;
+            case OP_SUM1F: acc = (w0 & TC_F_NEGA) ? -x : x; break;
+            case OP_SUM1: acc = __dadd_rn(acc, (w0 & TC_F_NEGA) ? -x : x); break;
+            case OP_PSET: p = __dmul_rn(x, y); break;                              // products of >2 factors
+            case OP_PMUL1: p = __dmul_rn(p, x); break;
+            case OP_PMUL2: p = __dmul_rn(__dmul_rn(p, x), y); break;
+            case OP_P1SET: acc = __dmul_rn(p, x); break;
+            case OP_P1ADD: acc = __dadd_rn(acc, __dmul_rn(p, x)); break;
+            case OP_P2SET: acc = __dmul_rn(__dmul_rn(p, x), y); break;
+            case OP_P2ADD: acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(p, x), y)); break;
+            default: acc = tc_cell_slow(op, w0, acc, x, y); break;
+            }
+            if (w0 & TC_F_END) {                                                   // warp-uniform
+                if (w0 & TC_F_NEG) acc = -acc;                                     // -(dot)       :1151-1164
+                ring[((w0 >> 16) & 0xffu) * TC_BLOCK] = acc;
+                if ((w0 & TC_F_STORE) && pred) mb[(size_t)cc[j].w * TC_TILE] = acc;
+            }
+        }
     }
 }
 
 // ---- lazy group evaluation and set/get/copy wrappers (writeCfunctionpergroup.m:513-852) ------
+// io[] word of a get/copy source: scratchbook slot, or constant-pool index when TC_CONST_BIT is set
+__device__ __forceinline__ double tc_ldop(const tc_lane &c, uint32_t w, bool pred) {
+    const uint32_t idx = w & TC_SLOT_MASK;
+    if (w & TC_CONST_BIT) return __ldg(c.consts + idx);                 // warp-uniform branch
+    return pred ? c.mb[(size_t)idx * TC_TILE] : 0.0;
+}
+
 __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image &P, const tc_func *f, bool pred) {
 #pragma unroll
     for (int w = 0; w < 2; w++) {
@@ -284,7 +242,7 @@ __device__ __forceinline__ void tc_invalidate(tc_lane &c, const tc_func *f, bool
 __device__ __forceinline__ void tc_set_scalar(tc_lane &c, const tc_device_image &P, int fn, double value, bool pred) {
     const tc_func *f = P.funcs + fn;
     uint32_t slot = __ldg(P.io + f->io_off);
-    if (pred) c.mb[(size_t)slot * (size_t)c.stride] = value;
+    if (pred) c.mb[(size_t)slot * TC_TILE] = value;
     tc_invalidate(c, f, pred);
 }
 
@@ -305,7 +263,7 @@ __device__ __noinline__ void tc_copy(tc_lane &c, const tc_device_image &P, int f
     for (uint32_t k = 0; k < cnt; k += 2) {
         uint32_t d = __ldg(io + k), s = __ldg(io + k + 1);
         double v = tc_ldop(c, s, pred);
-        if (pred) c.mb[(size_t)d * (size_t)c.stride] = v;
+        if (pred) c.mb[(size_t)d * TC_TILE] = v;
     }
     tc_invalidate(c, f, pred);
 }

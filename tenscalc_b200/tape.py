@@ -3,21 +3,31 @@
 This replaces the reference's C emitter (``writeCinstructionsC``,
 ``lib/csparse/instructionsTableUTHash.c:790-1609`` + the wrappers of
 ``writeCfunctionpergroup.m:513-852``): instead of C text compiled per problem, the
-straight-line code of every dependency group becomes a compact *tape* of 32-bit words
-that the generic kernels in ``csrc/`` interpret with one instance per lane, so the same
-pre-built ``.so`` serves any problem structure.
+straight-line code of every dependency group becomes a compact *tape* that the generic
+kernels in ``csrc/`` interpret with one instance per lane, so the same pre-built ``.so``
+serves any problem structure.
 
-Tape, per instruction::
+Tape = array of 128-bit CELLS.  A cell is one step of an accumulator machine with two
+registers per lane (``acc``, ``p``) and up to two memory operands::
 
-    word 0   opcode (bits 0-7, reference opcode numbers) | n_operands << 8
-    word 1   result slot
-    [word 2  m = factors per product, I_sumprod only]
-    ...      operand words: bits 0-29 scratch slot or constant-pool index,
-                            bit 30 = operand is a constant, bit 31 = negate (I_sum)
+    word 0   op (bits 0-7) | flags (bits 8-15) | ring slot of the result (bits 16-23)
+    word 1   operand A      bits 30-31 space (0 scratchbook slot, 1 constant pool, 2 result
+    word 2   operand B                        ring, 3 none), bits 0-29 index
+    word 3   scratchbook slot of the result (when F_STORE)
 
-The evaluation order inside an instruction is the C expression order of the reference
-emitter, and the kernels use separate multiply/add roundings,
-so results are bit-identical to the CPU oracle wherever no libm function is involved.
+An instruction of the reference ISA becomes 1..k cells; the LAST one
+carries F_END: the accumulator is the instruction's value, it is pushed into the per-lane
+RESULT RING (shared memory, the last RING results of the group) and, when F_STORE, written to
+the scratchbook.  The evaluation order inside an instruction is the C expression order of the
+reference emitter and the kernels round every multiply and add separately, so results are
+bit-identical to the CPU oracle wherever no libm function is involved.
+
+The kernels fetch scratchbook operands one BUNDLE (``BUNDLE`` cells) ahead of execution to
+keep ~2*BUNDLE loads in flight per warp.  That is only legal for operands that are not
+produced inside the look-ahead window: the lowering below redirects every operand whose
+producer is one of the previous ``RING`` results of the same group to the result ring, which
+covers the window (every instruction has at least one cell, and RING > 2*BUNDLE).  Values whose
+every use is served by the ring are never stored to the scratchbook at all.
 
 Image = 64 int64 header + 16 double header + sections (see ``serialize``).
 """
@@ -31,10 +41,29 @@ from . import itable as it
 from .csparse import CompiledProblem
 from .optimize import GeneratedSolver
 
-MAGIC = 0x3030324243540001  # "\x01\0TCB200" little-endian tag + format version
-CONST_BIT = 1 << 30
-NEG_BIT = 1 << 31
+MAGIC = 0x3030324243540002  # "\x02\0TCB200" little-endian tag + format version
+CONST_BIT = 1 << 30         # io[] words only (get/copy sources): constant-pool index
 NO_SLOT = 0xFFFFFFFF
+
+BUNDLE = 8                  # cells fetched/decoded together -- MUST match TC_BUNDLE in csrc/tc_vm.cuh
+RING = 32                   # results kept in the shared-memory ring -- MUST match TC_RING
+
+SP_SLOT, SP_CONST, SP_RING, SP_NONE = 0, 1, 2, 3
+OPERAND_NONE = SP_NONE << 30
+
+F_STORE = 1 << 8            # write the result to scratchbook slot word3
+F_END = 1 << 9              # last cell of an instruction: push acc to the ring
+F_NEG = 1 << 10             # result = -acc
+F_NEGA = 1 << 11            # operand A enters with a minus sign (I_sum)
+F_NEGB = 1 << 12            # operand B enters with a minus sign (I_sum)
+F_INIT = 1 << 13            # min0/max0: acc=0 first; clp: acc=DBL_MAX first
+
+# cell opcodes -- MUST match enum tc_cellop in csrc/tc_image.h
+(OP_NOP, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2, OP_MSET, OP_MADD, OP_PSET, OP_PMUL1, OP_PMUL2,
+ OP_P1SET, OP_P1ADD, OP_P2SET, OP_P2ADD, OP_RSUB, OP_RSUBDIV, OP_NEGDIV, OP_DIV, OP_SQ1F, OP_SQ2F,
+ OP_SQ1, OP_SQ2, OP_ABS1F, OP_ABS2F, OP_ABS1, OP_ABS2, OP_MINF1, OP_MINF2, OP_MIN1, OP_MIN2,
+ OP_MAXF1, OP_MAXF2, OP_MAX1, OP_MAX2, OP_AMAXF1, OP_AMAXF2, OP_AMAX1, OP_AMAX2, OP_CLP, OP_PACC) = range(40)
+OP_UNARY = 64               # + reference opcode of the unary function (I_inv ... I_heaviside)
 
 # driver function ids -- MUST match enum tc_fn in csrc/tc_image.h
 FN = {name: k for k, name in enumerate([
@@ -59,50 +88,185 @@ def _mask128(groups) -> Tuple[int, int]:
     return lo, hi
 
 
-def lower(gen: GeneratedSolver) -> Dict[str, np.ndarray]:
+def _pairs_first_rest(ops: List[int], first_op: int, next_op: int) -> List[Tuple[int, int, int, int]]:
+    """cells (op, flags, A, B) for a left-to-right sum of products of PAIRS"""
+    cells = []
+    for k in range(0, len(ops), 2):
+        cells.append((first_op if k == 0 else next_op, 0, ops[k], ops[k + 1]))
+    return cells
+
+
+def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
+    """Cells [op, flags, A, B] of one instruction; ``opw`` are the encoded operand words in the
+    reference's operand order.  The arithmetic order is that of the emitted C statement
+    (instructionsTableUTHash.c:950-1539)."""
+    N = OPERAND_NONE
+    c: List[List[int]] = []
+
+    def two(xs, f1, f2, n1, n2, flags_first=0):
+        """generic left-to-right fold over a list, two operands per cell"""
+        for k in range(0, len(xs), 2):
+            pair = xs[k:k + 2]
+            first = k == 0
+            if len(pair) == 2:
+                c.append([f2 if first else n2, flags_first if first else 0, pair[0], pair[1]])
+            else:
+                c.append([f1 if first else n1, flags_first if first else 0, pair[0], N])
+
+    def dot(xs):
+        for k in range(0, len(xs), 2):
+            c.append([OP_MSET if k == 0 else OP_MADD, 0, xs[k], xs[k + 1]])
+
+    if t in (it.I_load, it.I_2):
+        c.append([OP_SUM1F, 0, opw[0], N])
+    elif t == it.I_sum:                                          # +a-b+c...           :964-968
+        for k in range(0, len(opw), 2):
+            pair = opw[k:k + 2]
+            fl = (F_NEGA if p[k] < 0 else 0) | (F_NEGB if len(pair) == 2 and p[k + 1] < 0 else 0)
+            if len(pair) == 2:
+                c.append([OP_SUM2F if k == 0 else OP_SUM2, fl, pair[0], pair[1]])
+            else:
+                c.append([OP_SUM1F if k == 0 else OP_SUM1, fl, pair[0], N])
+    elif t == it.I_sumprod:                                      # a*b+c*d+...         :1007-1029
+        m = int(p[0])
+        if m == 1:
+            two(opw, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2)
+        elif m == 2:
+            dot(opw)
+        else:
+            for k in range(0, len(opw), m):
+                f = opw[k:k + m]
+                first = k == 0
+                c.append([OP_PSET, 0, f[0], f[1]])
+                rest = f[2:]
+                while len(rest) > 2:
+                    c.append([OP_PMUL2, 0, rest[0], rest[1]])
+                    rest = rest[2:]
+                if len(rest) == 2:
+                    c.append([OP_P2SET if first else OP_P2ADD, 0, rest[0], rest[1]])
+                else:
+                    c.append([OP_P1SET if first else OP_P1ADD, 0, rest[0], N])
+    elif t == it.I_plus_minus_dot_div:                           # (a0-(dot))/d        :1081-1098
+        dot(opw[2:])
+        c.append([OP_RSUBDIV, 0, opw[0], opw[1]])
+    elif t == it.I_minus_dot_div:                                # -(dot)/d            :1106-1121
+        dot(opw[1:])
+        c.append([OP_NEGDIV, 0, opw[0], N])
+    elif t == it.I_plus_minus_dot:                               # a0-(dot)            :1128-1144
+        dot(opw[1:])
+        c.append([OP_RSUB, 0, opw[0], N])
+    elif t == it.I_minus_dot:                                    # -(dot)              :1151-1164
+        dot(opw)
+        c[-1][1] |= F_NEG
+    elif t == it.I_div:
+        c.append([OP_DIV, 0, opw[0], opw[1]])
+    elif t == it.I_plus_sqr:                                     # a*a+b*b+...         :1201-1210
+        two(opw, OP_SQ1F, OP_SQ2F, OP_SQ1, OP_SQ2)
+    elif t == it.I_plus_abs:                                     # |a|+|b|+...         :1217-1225
+        two(opw, OP_ABS1F, OP_ABS2F, OP_ABS1, OP_ABS2)
+    elif t == it.I_min:                                          # compare chains      :1228-1313
+        two(opw, OP_MINF1, OP_MINF2, OP_MIN1, OP_MIN2)
+    elif t == it.I_max:
+        two(opw, OP_MAXF1, OP_MAXF2, OP_MAX1, OP_MAX2)
+    elif t == it.I_min0:                                         # acc=0, then the chain
+        two(opw, OP_MIN1, OP_MIN2, OP_MIN1, OP_MIN2, flags_first=F_INIT)
+    elif t == it.I_max0:
+        two(opw, OP_MAX1, OP_MAX2, OP_MAX1, OP_MAX2, flags_first=F_INIT)
+    elif t == it.I_max_abs:
+        two(opw, OP_AMAXF1, OP_AMAXF2, OP_AMAX1, OP_AMAX2)
+    elif t == it.I_clp:                                          # :1315-1331
+        for k in range(0, len(opw), 2):
+            c.append([OP_CLP, F_INIT if k == 0 else 0, opw[k], opw[k + 1]])
+    elif t in it.UNARY_TYPES:
+        c.append([OP_UNARY + t, 0, opw[0], N])
+    else:
+        raise NotImplementedError(it.OPNAMES.get(t, str(t)))
+    c[-1][1] |= F_END
+    return c
+
+
+def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[str, np.ndarray]:
     pr: CompiledProblem = gen.problem
     tab, slot = pr.tab, pr.slot
     if pr.n_slots >= CONST_BIT:
         raise ValueError("scratchbook too large for the 30-bit slot field")
+    if ring <= 2 * bundle:
+        raise ValueError("the result ring must cover the operand look-ahead window (RING > 2*BUNDLE)")
     consts: List[float] = []
     cindex: Dict[float, int] = {}
 
-    def cword(v: float) -> int:
+    def cidx(v: float) -> int:
         k = cindex.get(v)
         if k is None:
             k = cindex[v] = len(consts)
             consts.append(v)
-        return CONST_BIT | k
+        return k
 
-    def opword(i: int) -> int:
+    def const_of(i: int):
         t = tab.types[i]
         if t == it.I_load:
-            return cword(tab.params[i][0])
+            return tab.params[i][0]
         if t == it.I_2:
-            return cword(2.0)
-        return int(slot[i])
+            return 2.0
+        return None
 
-    tape: List[int] = []
+    def io_word(i: int) -> int:                 # get/copy sources: slot or constant
+        v = const_of(i)
+        return (CONST_BIT | cidx(v)) if v is not None else int(slot[i])
+
+    # values that must reach the scratchbook: read by another group, a get or a copy
+    external = set()
+    for g in pr.gets.values():
+        external.update(x for s in g.sources for x in s if x is not None)
+    for c in pr.copies.values():
+        external.update(c.src)
+    for i, gi in pr.group_of.items():
+        for o in tab.operands[i]:
+            if pr.group_of.get(o, -1) != gi:
+                external.add(o)
+
+    cells: List[List[int]] = []                 # [w0, w1, w2, w3]
     group_start = [0]
-    operand_reads = []          # per group: scratch operand loads (constants excluded)
+    stats = dict(slot_reads=0, ring_reads=0, const_reads=0, stores=0, ring_only=0)
     for members in pr.groups:
-        reads = 0
-        for i in members:
+        order = {i: n for n, i in enumerate(members)}
+        # furthest in-group consumer of every result, in results
+        far = {}
+        for n, i in enumerate(members):
+            for o in tab.operands[i]:
+                k = order.get(o)
+                if k is not None:
+                    far[o] = max(far.get(o, 0), n - k)
+        for n, i in enumerate(members):
             t, p, ops = tab.types[i], tab.params[i], tab.operands[i]
             if t in (it.I_load, it.I_2):
-                words = [cword(p[0] if t == it.I_load else 2.0)]
-                tape += [it.I_sum | (1 << 8), int(slot[i])] + words
-                continue
-            words = [opword(o) for o in ops]
-            if t == it.I_sum:
-                words = [w | (NEG_BIT if s < 0 else 0) for w, s in zip(words, p)]
-            tape += [t | (len(words) << 8), int(slot[i])]
-            if t == it.I_sumprod:
-                tape.append(int(p[0]))
-            tape += words
-            reads += sum(1 for w in words if not w & CONST_BIT)
-        group_start.append(len(tape))
-        operand_reads.append(reads)
+                opw = [(SP_CONST << 30) | cidx(const_of(i))]
+                stats["const_reads"] += 1
+            else:
+                opw = []
+                for o in ops:
+                    v = const_of(o)
+                    k = order.get(o)
+                    if v is not None:
+                        opw.append((SP_CONST << 30) | cidx(v))
+                        stats["const_reads"] += 1
+                    elif k is not None and n - k < ring:
+                        opw.append((SP_RING << 30) | (k % ring))
+                        stats["ring_reads"] += 1
+                    else:
+                        opw.append((SP_SLOT << 30) | int(slot[o]))
+                        stats["slot_reads"] += 1
+            cs = instruction_cells(t, p, opw)
+            store = i in external or far.get(i, 0) >= ring
+            last = cs[-1]
+            last[1] |= F_STORE if store else 0
+            stats["stores" if store else "ring_only"] += 1
+            for op, fl, a, b in cs[:-1]:
+                cells.append([op | fl, a, b, 0])
+            cells.append([last[0] | last[1] | ((n % ring) << 16), last[2], last[3], int(slot[i]) if store else 0])
+        while len(cells) % bundle:
+            cells.append([OP_NOP, OPERAND_NONE, OPERAND_NONE, 0])
+        group_start.append(len(cells))
 
     # ---- function table ------------------------------------------------------------------------
     user_sets = [s for s in pr.sets.values() if s.kind in ("parameter", "variable")]
@@ -117,7 +281,7 @@ def lower(gen: GeneratedSolver) -> Dict[str, np.ndarray]:
         io.extend(words)
 
     def src_word(x) -> int:
-        return NO_SLOT if x is None else opword(x)
+        return NO_SLOT if x is None else io_word(x)
 
     for name, fid in FN.items():
         if name in pr.sets:
@@ -142,11 +306,12 @@ def lower(gen: GeneratedSolver) -> Dict[str, np.ndarray]:
         set_fids.append(FN_USER0 + k)
     out_sizes = [int(np.prod(s)) if s else 1 for _, s in gen.outputs]
 
-    return dict(tape=np.asarray(tape, dtype=np.uint32), group_start=np.asarray(group_start, dtype=np.uint32),
+    return dict(tape=np.asarray(cells, dtype=np.uint32).reshape(-1, 4),
+                group_start=np.asarray(group_start, dtype=np.uint32),
                 consts=np.asarray(consts if consts else [0.0], dtype=np.float64), funcs=funcs,
                 io=np.asarray(io if io else [0], dtype=np.uint32),
                 set_fids=np.asarray(set_fids, dtype=np.uint32), out_sizes=np.asarray(out_sizes, dtype=np.uint32),
-                operand_reads=np.asarray(operand_reads, dtype=np.int64))
+                stats=stats)
 
 
 def serialize(gen: GeneratedSolver) -> bytes:
@@ -156,6 +321,7 @@ def serialize(gen: GeneratedSolver) -> bytes:
     ih[0] = MAGIC
     ih[1:9] = (gen.problem.n_slots, len(gen.problem.groups), len(L["funcs"]), len(L["set_fids"]),
                len(L["out_sizes"]), len(L["tape"]), len(L["consts"]), len(L["io"]))
+    ih[9:11] = (RING, BUNDLE)
     ih[16:19] = (d["nU"], d["nG"], d["nF"])
     ih[19:27] = (d["scaleCost"], d["scaleInequalities"], d["coupledAlphas"], d["setAddEye2Hessian"],
                  d["adjustAddEye2Hessian"], d["useInertia"], d["skipAffine"], d["delta"])
@@ -163,10 +329,10 @@ def serialize(gen: GeneratedSolver) -> bytes:
     dh[0:8] = (d["gradTolerance"], d["addEye2HessianUtolerance"], d["equalTolerance"], d["desiredDualityGap"],
                d["alphaMin"], d["alphaMax"], d["muFactorAggressive"], d["muFactorConservative"])
 
-    def pad8(b: bytes) -> bytes:
-        return b + b"\0" * (-len(b) % 8)
+    def pad16(b: bytes) -> bytes:
+        return b + b"\0" * (-len(b) % 16)
 
     parts = [ih.tobytes(), dh.tobytes()]
     for key in ("group_start", "tape", "consts", "funcs", "io", "set_fids", "out_sizes"):
-        parts.append(pad8(np.ascontiguousarray(L[key]).tobytes()))
+        parts.append(pad16(np.ascontiguousarray(L[key]).tobytes()))
     return b"".join(parts)

@@ -155,33 +155,35 @@ def test_memory_map_never_aliases_live_values():
         assert owner.get(int(slot[i]), i) == i or tab.types[i] == it.I_set
 
 
-def test_tape_decodes_back_to_the_instruction_list():
-    from tenscalc_b200 import tape
-    gen, _ = generated("sls")
+def test_tape_structure():
+    """groups start on bundle boundaries, every instruction ends in exactly one F_END cell, ring
+    operands always point at one of the previous RING results, look-ahead operands are never
+    produced inside the look-ahead window"""
+    from tenscalc_b200 import tape as tp
+    gen, _ = generated("mpc_dcmotor")
     pr = gen.problem
-    L = tape.lower(gen)
-    words = L["tape"]
-    pc = 0
+    L = tp.lower(gen)
+    cells, gs = L["tape"], L["group_start"]
+    assert len(cells) % tp.BUNDLE == 0 and all(int(x) % tp.BUNDLE == 0 for x in gs)
     for g, members in enumerate(pr.groups):
-        assert pc == L["group_start"][g]
-        for i in members:
-            hdr, r = int(words[pc]), int(words[pc + 1])
-            op, n = hdr & 0xFF, hdr >> 8
-            pc += 2
-            t = pr.tab.types[i]
-            if t in (it.I_load, it.I_2):
-                assert op == it.I_sum and n == 1 and words[pc] & tape.CONST_BIT
-            else:
-                assert op == t and n == len(pr.tab.operands[i]) and r == pr.slot[i]
-                if t == it.I_sumprod:
-                    assert words[pc] == int(pr.tab.params[i][0])
-                    pc += 1
-                for k, o in enumerate(pr.tab.operands[i]):
-                    w = int(words[pc + k])
-                    if not w & tape.CONST_BIT:
-                        assert (w & 0x3FFFFFFF) == pr.slot[o]
-            pc += n
-    assert pc == len(words) == L["group_start"][-1]
+        grp = cells[int(gs[g]):int(gs[g + 1])]
+        ends = [k for k, c in enumerate(grp) if int(c[0]) & tp.F_END]
+        assert len(ends) == len(members)
+        produced_at = {}                      # slot -> cell index of its store
+        n = 0
+        for k, c in enumerate(grp):
+            for w in (int(c[1]), int(c[2])):
+                if (w >> 30) == tp.SP_SLOT and w in produced_at:
+                    # fetched when the previous bundle starts executing
+                    fetch_time = (k // tp.BUNDLE - 1) * tp.BUNDLE
+                    assert produced_at[w] < fetch_time, "look-ahead operand produced inside the window"
+                if (w >> 30) == tp.SP_RING:
+                    assert (w & 0xFF) < tp.RING
+            if int(c[0]) & tp.F_END:
+                assert ((int(c[0]) >> 16) & 0xFF) == n % tp.RING
+                if int(c[0]) & tp.F_STORE:
+                    produced_at[int(c[3])] = k
+                n += 1
 
 
 def test_reference_rejected_options_raise():
@@ -202,3 +204,147 @@ def test_problem_sizes_match_survey_table():
         gen, _ = generated(name)
         d = gen.defines
         assert (d["nU"], d["nG"], d["nF"]) == (nU, nG, nF), name
+
+
+def _emulate_cells(L, g, m, consts, ring_size):
+    """numpy model of csrc/tc_vm.cuh::tc_exec_group (one lane per batch entry): fetches the
+    scratchbook operands of bundle b+1 BEFORE executing bundle b, exactly like the kernel, so a
+    lowering that let a look-ahead operand be produced inside the window would be caught here"""
+    from tenscalc_b200 import tape as tp
+    from oracle.pyeval import _UNARY
+    cells = L["tape"]
+    lo, hi = int(L["group_start"][g]), int(L["group_start"][g + 1])
+    B = m.shape[1]
+    ring = np.zeros((ring_size, B))
+    acc = np.zeros(B)
+    p = np.zeros(B)
+    U = tp.BUNDLE
+
+    def fetch(b):
+        out = []
+        for j in range(U):
+            c = cells[lo + b * U + j]
+            out.append([m[int(w) & 0x3FFFFFFF].copy() if (int(w) >> 30) == tp.SP_SLOT else None for w in (c[1], c[2])])
+        return out
+    nb = (hi - lo) // U
+    nxt = fetch(0)
+    with np.errstate(all="ignore"):
+        for b in range(nb):
+            cur = nxt
+            if b + 1 < nb:
+                nxt = fetch(b + 1)
+            for j in range(U):
+                w0, wa, wb, wr = [int(v) for v in cells[lo + b * U + j]]
+                op = w0 & 0xFF
+
+                def late(w, v):
+                    sp = w >> 30
+                    if sp == tp.SP_RING:
+                        return ring[w & 0xFF].copy()
+                    if sp == tp.SP_CONST:
+                        return np.full(B, consts[w & 0x3FFFFFFF])
+                    return v
+                x, y = late(wa, cur[j][0]), late(wb, cur[j][1])
+                sx = (lambda v: -v) if w0 & tp.F_NEGA else (lambda v: v)
+                sy = (lambda v: -v) if w0 & tp.F_NEGB else (lambda v: v)
+                init = bool(w0 & tp.F_INIT)
+                if op == tp.OP_NOP: pass
+                elif op == tp.OP_SUM1F: acc = sx(x)
+                elif op == tp.OP_SUM2F: acc = sx(x) + sy(y)
+                elif op == tp.OP_SUM1: acc = acc + sx(x)
+                elif op == tp.OP_SUM2: acc = (acc + sx(x)) + sy(y)
+                elif op == tp.OP_MSET: acc = x * y
+                elif op == tp.OP_MADD: acc = acc + x * y
+                elif op == tp.OP_PSET: p = x * y
+                elif op == tp.OP_PMUL1: p = p * x
+                elif op == tp.OP_PMUL2: p = (p * x) * y
+                elif op == tp.OP_P1SET: acc = p * x
+                elif op == tp.OP_P1ADD: acc = acc + p * x
+                elif op == tp.OP_P2SET: acc = (p * x) * y
+                elif op == tp.OP_P2ADD: acc = acc + (p * x) * y
+                elif op == tp.OP_RSUB: acc = x - acc
+                elif op == tp.OP_RSUBDIV: acc = (x - acc) / y
+                elif op == tp.OP_NEGDIV: acc = (-acc) / x
+                elif op == tp.OP_DIV: acc = x / y
+                elif op == tp.OP_SQ1F: acc = x * x
+                elif op == tp.OP_SQ2F: acc = x * x + y * y
+                elif op == tp.OP_SQ1: acc = acc + x * x
+                elif op == tp.OP_SQ2: acc = (acc + x * x) + y * y
+                elif op == tp.OP_ABS1F: acc = np.abs(x)
+                elif op == tp.OP_ABS2F: acc = np.abs(x) + np.abs(y)
+                elif op == tp.OP_ABS1: acc = acc + np.abs(x)
+                elif op == tp.OP_ABS2: acc = (acc + np.abs(x)) + np.abs(y)
+                elif op in (tp.OP_MINF1, tp.OP_MAXF1): acc = x
+                elif op == tp.OP_AMAXF1: acc = np.abs(x)
+                elif op in (tp.OP_MINF2, tp.OP_MIN1, tp.OP_MIN2, tp.OP_MAXF2, tp.OP_MAX1, tp.OP_MAX2,
+                            tp.OP_AMAXF2, tp.OP_AMAX1, tp.OP_AMAX2):
+                    is_min = op in (tp.OP_MINF2, tp.OP_MIN1, tp.OP_MIN2)
+                    f = np.abs if op in (tp.OP_AMAXF2, tp.OP_AMAX1, tp.OP_AMAX2) else (lambda v: v)
+                    vals = [x] if op in (tp.OP_MIN1, tp.OP_MAX1, tp.OP_AMAX1) else [x, y]
+                    if op in (tp.OP_MINF2, tp.OP_MAXF2, tp.OP_AMAXF2):
+                        acc, vals = f(x), [y]
+                    elif init:
+                        acc = np.zeros(B)
+                    for v in vals:
+                        take = (acc > f(v)) if is_min else (acc < f(v))
+                        acc = np.where(take, f(v), acc)
+                elif op == tp.OP_CLP:
+                    if init:
+                        acc = np.full(B, np.finfo(float).max)
+                    q = (-x) / y
+                    acc = np.where((y < 0) & (acc > q), q, acc)
+                elif op >= tp.OP_UNARY:
+                    acc = _UNARY[op - tp.OP_UNARY](x)
+                else:
+                    raise AssertionError(op)
+                if w0 & tp.F_END:
+                    if w0 & tp.F_NEG:
+                        acc = -acc
+                    ring[(w0 >> 16) & 0xFF] = acc
+                    if w0 & tp.F_STORE:
+                        m[wr] = acc
+
+
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor", "mpc_quadcopter"])
+def test_cell_tape_equals_instruction_semantics(name):
+    """every group: numpy model of the kernel's cell machine (with its look-ahead operand fetch)
+    vs direct evaluation of the reference instruction forms (oracle/pyeval.py), bit for bit"""
+    from tenscalc_b200 import tape as tp
+    from oracle.pyeval import eval_instruction
+    gen, _ = generated(name)
+    pr = gen.problem
+    tab, slot = pr.tab, pr.slot
+    L = tp.lower(gen)
+    B = 3
+    rng = np.random.default_rng(5)
+    groups = range(len(pr.groups)) if name != "mpc_quadcopter" else \
+        sorted(range(len(pr.groups)), key=lambda g: -len(pr.groups[g]))[:4]
+    external = set()
+    for gdecl in pr.gets.values():
+        external.update(x for s in gdecl.sources for x in s if x is not None)
+    for c in pr.copies.values():
+        external.update(c.src)
+    for i, gi in pr.group_of.items():
+        external.update(o for o in tab.operands[i] if pr.group_of.get(o, -1) != gi)
+    for g in groups:
+        members = pr.groups[g]
+        m0 = rng.uniform(.5, 1.5, size=(pr.n_slots, B)) * rng.choice([-1, 1], size=(pr.n_slots, B))
+        # (a) instruction semantics, values keyed by instruction id; operands outside the group
+        # come from the scratchbook
+        v = {}
+        mset = set(members)
+        with np.errstate(all="ignore"):
+            for i in members:
+                for o in tab.operands[i]:
+                    if o not in v and o not in mset and tab.types[o] not in (it.I_load, it.I_2):
+                        v[o] = m0[slot[o]].copy()
+                    elif o not in v and tab.types[o] in (it.I_load, it.I_2):
+                        v[o] = eval_instruction(tab, o, v, B)
+                v[i] = eval_instruction(tab, i, v, B)
+        # (b) cell machine
+        m = m0.copy()
+        _emulate_cells(L, g, m, L["consts"], tp.RING)
+        for i in members:
+            if i in external:
+                a, b = m[slot[i]], v[i]
+                assert np.array_equal(a, b, equal_nan=True), (name, g, i, it.OPNAMES[tab.types[i]])
