@@ -13,8 +13,11 @@
 // kernels
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &P, int64_t inst) {
-    __shared__ double ring[TC_RING * TC_BLOCK];     // result ring, [slot][thread]: conflict-free
-    c.ring = ring + threadIdx.x;
+    // result ring [slot][thread] (conflict-free), then the constant pool (broadcast reads)
+    __shared__ double sm[TC_RING_DOUBLES + TC_MAXCONST];
+    for (int k = threadIdx.x; k < P.n_consts; k += TC_BLOCK) sm[TC_RING_DOUBLES + k] = P.consts[k];
+    __syncthreads();
+    c.sm = sm;
     c.mb = &TC_M(P, 0, inst);
     c.consts = P.consts;
     c.tape = P.tape;
@@ -29,7 +32,7 @@ __device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device
 }
 
 // whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
-__global__ void __launch_bounds__(TC_BLOCK, 3) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
+__global__ void __launch_bounds__(TC_BLOCK, 4) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
                                                             double aeU, double aeEq,
                                                             int32_t *__restrict__ status,
                                                             int32_t *__restrict__ iter) {
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(TC_BLOCK, 3) tc_solve_kernel(tc_device_image P
 }
 
 // lazy evaluation of the parents of one get function (classname_getOutputs)
-__global__ void __launch_bounds__(TC_BLOCK, 3) tc_eval_kernel(tc_device_image P, int fn) {
+__global__ void __launch_bounds__(TC_BLOCK, 4) tc_eval_kernel(tc_device_image P, int fn) {
     const int64_t inst = (int64_t)blockIdx.x * TC_BLOCK + threadIdx.x;
     tc_lane c;
     tc_lane_init(c, P, inst);
@@ -196,7 +199,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     const uint32_t *set_fids = (const uint32_t *)p;    p += pad16(n_sets * 4);
     const uint32_t *out_sizes = (const uint32_t *)p;   p += pad16(n_out * 4);
     if ((size_t)(p - (const char *)image) > image_bytes || n_groups > 128 || ih[9] != TC_RING ||
-        ih[10] != TC_BUNDLE || tape_cells % TC_BUNDLE) {
+        ih[10] != TC_BUNDLE || tape_cells % TC_BUNDLE || n_consts > TC_MAXCONST) {
         delete s;
         return TC_EFORMAT;
     }
@@ -236,6 +239,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     I.n_slots = n_slots;
     I.batch = batch;
     I.n_groups = (int32_t)n_groups;
+    I.n_consts = (int32_t)n_consts;
     tc_defines &D = I.def;
     D.nU = (int32_t)ih[16]; D.nG = (int32_t)ih[17]; D.nF = (int32_t)ih[18];
     D.scaleCost = (int32_t)ih[19]; D.scaleInequalities = (int32_t)ih[20]; D.coupledAlphas = (int32_t)ih[21];

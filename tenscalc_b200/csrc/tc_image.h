@@ -4,33 +4,35 @@
 #include <stdint.h>
 #include <vector_types.h>
 
-#define TC_MAGIC 0x3030324243540002LL
+#define TC_MAGIC 0x3030324243540003LL
 #define TC_CONST_BIT 0x40000000u   // io[] words (get/copy sources): constant-pool index
 #define TC_SLOT_MASK 0x3FFFFFFFu
 #define TC_NO_SLOT 0xFFFFFFFFu
-#define TC_BUNDLE 8                // cells fetched together        -- MUST match tape.py BUNDLE
-#define TC_RING 32                 // results in the per-lane ring  -- MUST match tape.py RING
+#define TC_TILE 32                 // instances per scratchbook tile = lanes per warp
+#define TC_BLOCK 128               // threads per CTA = instances per CTA -- MUST match tape.py BLOCK
+#define TC_BUNDLE 4                // cells fetched together               -- MUST match tape.py BUNDLE
+#define TC_RING 32                 // results in the per-lane ring         -- MUST match tape.py RING
+#define TC_MAXCONST 1024           // constant pool in shared memory       -- MUST match tape.py MAX_CONSTS
+#define TC_RING_DOUBLES (TC_RING * TC_BLOCK)
 
-// tape cell = uint4 {op|flags|ring slot<<16, operand A, operand B, result slot}; see tape.py
-#define TC_SP_SLOT 0u
-#define TC_SP_CONST 1u
-#define TC_SP_RING 2u
-#define TC_SP_NONE 3u
-#define TC_F_STORE (1u << 8)
-#define TC_F_END (1u << 9)
-#define TC_F_NEG (1u << 10)
-#define TC_F_NEGA (1u << 11)
-#define TC_F_NEGB (1u << 12)
-#define TC_F_INIT (1u << 13)
+// tape cell = uint4 {op|flags|ring slot<<16, operand A, operand B, result offset}; see tape.py
+#define TC_F_ALATE (1u << 7)
+#define TC_F_BLATE (1u << 8)
+#define TC_F_STORE (1u << 9)
+#define TC_F_END (1u << 10)
+#define TC_F_NEG (1u << 11)
+#define TC_F_NEGA (1u << 12)
+#define TC_F_NEGB (1u << 13)
+#define TC_F_INIT (1u << 14)
+#define TC_F_FIRST (1u << 15)
 
 enum tc_cellop {   // MUST match the OP_* list of tenscalc_b200/tape.py
-    OP_NOP = 0, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2, OP_MSET, OP_MADD, OP_PSET, OP_PMUL1, OP_PMUL2,
+    OP_MADD = 0, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2, OP_NOP, OP_RESERVED, OP_PSET, OP_PMUL1, OP_PMUL2,
     OP_P1SET, OP_P1ADD, OP_P2SET, OP_P2ADD, OP_RSUB, OP_RSUBDIV, OP_NEGDIV, OP_DIV, OP_SQ1F, OP_SQ2F,
     OP_SQ1, OP_SQ2, OP_ABS1F, OP_ABS2F, OP_ABS1, OP_ABS2, OP_MINF1, OP_MINF2, OP_MIN1, OP_MIN2,
     OP_MAXF1, OP_MAXF2, OP_MAX1, OP_MAX2, OP_AMAXF1, OP_AMAXF2, OP_AMAX1, OP_AMAX2, OP_CLP, OP_PACC,
     OP_UNARY = 64   // + reference opcode of the unary function
 };
-#define TC_TILE 32   // instances per scratchbook tile = lanes per warp
 
 // driver function ids -- MUST match FN in tenscalc_b200/tape.py.  Names are the reference's
 // (lib/ipmPD_CStimesLambda.m declares them, lib/ipmPD_CSsolver.c:28-51 calls them).
@@ -83,6 +85,7 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     int64_t stride;         // padded batch (multiple of 32)
     int64_t batch;
     int32_t n_groups;
+    int32_t n_consts;
     tc_defines def;
 };
 

@@ -26,13 +26,12 @@
 #include "tc_image.h"
 
 #define TC_FULL 0xFFFFFFFFu
-#define TC_BLOCK 128   // threads per CTA = instances per CTA; the batch stride is a multiple of it
 
 struct tc_lane {
     double *mb;            // &m[tile][0][lane]; slot k of this instance is mb[k*32]
     const double *consts;
     const uint4 *tape;
-    double *ring;          // shared memory, &ring[0][thread]; result k lives at ring[k*TC_BLOCK]
+    double *sm;            // shared memory of the CTA: result ring [TC_RING][TC_BLOCK], then constants
     unsigned lane;
     uint64_t st[2];        // groupStatus[] of this instance, one bit per group
 };
@@ -76,130 +75,132 @@ __device__ __forceinline__ double tc_unary(int op, double x) {
     return x;
 }
 
-// rare cell kinds, kept out of line so that the hot dispatch stays small
-__device__ __noinline__ double tc_cell_slow(unsigned op, unsigned w0, double acc, double x, double y) {
+// every cell kind except OP_MADD, out of line so that the hot path stays small
+__device__ __noinline__ double2 tc_cell_other(unsigned w0, double acc, double p, double x, double y) {
+    const unsigned op = w0 & 0x7fu;
+    const double sx = (w0 & TC_F_NEGA) ? -x : x, sy = (w0 & TC_F_NEGB) ? -y : y;
     switch (op) {
-    case OP_SQ1F: return __dmul_rn(x, x);                              // a*a+b*b+...   :1201-1210
-    case OP_SQ2F: return __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
-    case OP_SQ1: return __dadd_rn(acc, __dmul_rn(x, x));
-    case OP_SQ2: return __dadd_rn(__dadd_rn(acc, __dmul_rn(x, x)), __dmul_rn(y, y));
-    case OP_ABS1F: return fabs(x);                                     // |a|+|b|+...   :1217-1225
-    case OP_ABS2F: return __dadd_rn(fabs(x), fabs(y));
-    case OP_ABS1: return __dadd_rn(acc, fabs(x));
-    case OP_ABS2: return __dadd_rn(__dadd_rn(acc, fabs(x)), fabs(y));
+    case OP_NOP: break;
+    case OP_SUM2F: acc = __dadd_rn(sx, sy); break;                          // +a-b+c...    :964-968
+    case OP_SUM2: acc = __dadd_rn(__dadd_rn(acc, sx), sy); break;
+    case OP_SUM1F: acc = sx; break;
+    case OP_SUM1: acc = __dadd_rn(acc, sx); break;
+    case OP_PSET: p = __dmul_rn(x, y); break;                               // products of >2 factors :1007-1029
+    case OP_PMUL1: p = __dmul_rn(p, x); break;
+    case OP_PMUL2: p = __dmul_rn(__dmul_rn(p, x), y); break;
+    case OP_P1SET: acc = __dmul_rn(p, x); break;
+    case OP_P1ADD: acc = __dadd_rn(acc, __dmul_rn(p, x)); break;
+    case OP_P2SET: acc = __dmul_rn(__dmul_rn(p, x), y); break;
+    case OP_P2ADD: acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(p, x), y)); break;
+    case OP_RSUBDIV: acc = __dadd_rn(x, -acc) / y; break;                   // (a0-(dot))/d :1081-1098
+    case OP_RSUB: acc = __dadd_rn(x, -acc); break;                          // a0-(dot)     :1128-1144
+    case OP_NEGDIV: acc = (-acc) / x; break;                                // -(dot)/d     :1106-1121
+    case OP_DIV: acc = x / y; break;
+    case OP_SQ1F: acc = __dmul_rn(x, x); break;                             // a*a+b*b+...  :1201-1210
+    case OP_SQ2F: acc = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)); break;
+    case OP_SQ1: acc = __dadd_rn(acc, __dmul_rn(x, x)); break;
+    case OP_SQ2: acc = __dadd_rn(__dadd_rn(acc, __dmul_rn(x, x)), __dmul_rn(y, y)); break;
+    case OP_ABS1F: acc = fabs(x); break;                                    // |a|+|b|+...  :1217-1225
+    case OP_ABS2F: acc = __dadd_rn(fabs(x), fabs(y)); break;
+    case OP_ABS1: acc = __dadd_rn(acc, fabs(x)); break;
+    case OP_ABS2: acc = __dadd_rn(__dadd_rn(acc, fabs(x)), fabs(y)); break;
     // sequential compare chains (:1228-1313): a NaN in a non-first operand is dropped
-    case OP_MINF1: return x;
-    case OP_MINF2: acc = x; if (acc > y) acc = y; return acc;
-    case OP_MIN2: if (w0 & TC_F_INIT) acc = 0.0; if (acc > x) acc = x; if (acc > y) acc = y; return acc;
-    case OP_MIN1: if (w0 & TC_F_INIT) acc = 0.0; if (acc > x) acc = x; return acc;
-    case OP_MAXF1: return x;
-    case OP_MAXF2: acc = x; if (acc < y) acc = y; return acc;
-    case OP_MAX2: if (w0 & TC_F_INIT) acc = 0.0; if (acc < x) acc = x; if (acc < y) acc = y; return acc;
-    case OP_MAX1: if (w0 & TC_F_INIT) acc = 0.0; if (acc < x) acc = x; return acc;
-    case OP_AMAXF1: return fabs(x);
-    case OP_AMAXF2: acc = fabs(x); if (acc < fabs(y)) acc = fabs(y); return acc;
-    case OP_AMAX2: if (acc < fabs(x)) acc = fabs(x); if (acc < fabs(y)) acc = fabs(y); return acc;
-    case OP_AMAX1: if (acc < fabs(x)) acc = fabs(x); return acc;
-    case OP_CLP:                                                       // :1315-1331
+    case OP_MINF1: acc = x; break;
+    case OP_MINF2: acc = x; if (acc > y) acc = y; break;
+    case OP_MIN2: if (w0 & TC_F_INIT) acc = 0.0; if (acc > x) acc = x; if (acc > y) acc = y; break;
+    case OP_MIN1: if (w0 & TC_F_INIT) acc = 0.0; if (acc > x) acc = x; break;
+    case OP_MAXF1: acc = x; break;
+    case OP_MAXF2: acc = x; if (acc < y) acc = y; break;
+    case OP_MAX2: if (w0 & TC_F_INIT) acc = 0.0; if (acc < x) acc = x; if (acc < y) acc = y; break;
+    case OP_MAX1: if (w0 & TC_F_INIT) acc = 0.0; if (acc < x) acc = x; break;
+    case OP_AMAXF1: acc = fabs(x); break;
+    case OP_AMAXF2: acc = fabs(x); if (acc < fabs(y)) acc = fabs(y); break;
+    case OP_AMAX2: if (acc < fabs(x)) acc = fabs(x); if (acc < fabs(y)) acc = fabs(y); break;
+    case OP_AMAX1: if (acc < fabs(x)) acc = fabs(x); break;
+    case OP_CLP:                                                            // :1315-1331
         if (w0 & TC_F_INIT) acc = DBL_MAX;
         if (y < 0) {
             double q = (-x) / y;
             if (acc > q) acc = q;
         }
-        return acc;
-    case OP_DIV: return x / y;
-    case OP_NEGDIV: return (-acc) / x;                                 // -(dot)/d      :1106-1121
-    default: return tc_unary((int)op - OP_UNARY, x);
+        break;
+    default: acc = tc_unary((int)op - OP_UNARY, x); break;
+    }
+    return make_double2(acc, p);
+}
+
+struct tc_bundle {                 // one bundle in flight: cells and their early (scratchbook) operands
+    uint4 c[TC_BUNDLE];
+    double x[TC_BUNDLE], y[TC_BUNDLE];
+};
+
+// Look-ahead fetch: scratchbook operands only, one predicated load each, no branches -- the
+// 2*TC_BUNDLE loads of a bundle issue back to back and stay in flight while the previous
+// bundle executes.
+__device__ __forceinline__ void tc_fetch(tc_bundle &B, const uint4 *cells, const char *mb, bool pred) {
+#pragma unroll
+    for (int j = 0; j < TC_BUNDLE; j++) B.c[j] = __ldg(cells + j);
+#pragma unroll
+    for (int j = 0; j < TC_BUNDLE; j++) {
+        const unsigned w0 = B.c[j].x;
+        double x = 0.0, y = 0.0;
+        if (pred && !(w0 & TC_F_ALATE)) x = *(const double *)(mb + B.c[j].y);
+        if (pred && !(w0 & TC_F_BLATE)) y = *(const double *)(mb + B.c[j].z);
+        B.x[j] = x;
+        B.y[j] = y;
     }
 }
 
-// Operand fetch, look-ahead part: scratchbook slots only, one predicated load each (no branch,
-// so the 2*TC_BUNDLE loads of a bundle issue back to back).  Constants (~1% of operands) and
-// ring operands are read at execution time.
-__device__ __forceinline__ double tc_fetch(const double *mb, unsigned w, bool pred) {
-    double v = 0.0;
-    if (pred && (w >> 30) == TC_SP_SLOT) v = mb[(size_t)w * TC_TILE];   // space 0: w == slot index
-    return v;
+// late operand: shared memory.  Word = byte offset | 1 for per-thread data (result ring),
+// even for CTA-wide data (constants); tid8m1 = 8*threadIdx.x-1.
+__device__ __forceinline__ double tc_late(const double *sm, unsigned w, unsigned tid8m1) {
+    return sm[(w + (w & 1u) * tid8m1) >> 3];
 }
 
-// execution-time operands: result ring (shared memory) or constant pool; warp-uniform branches
-__device__ __forceinline__ double tc_late(const tc_lane &c, const double *ring, unsigned w, double v) {
-    const unsigned sp = w >> 30;
-    if (sp == TC_SP_RING) v = ring[(w & 0xffu) * TC_BLOCK];
-    else if (sp == TC_SP_CONST) v = __ldg(c.consts + (w & TC_SLOT_MASK));
-    return v;
+__device__ __forceinline__ void tc_exec(const tc_bundle &B, char *mb, double *sm, unsigned tid, bool pred,
+                                        double &acc, double &p) {
+    const unsigned tid8m1 = 8u * tid - 1u;
+#pragma unroll
+    for (int j = 0; j < TC_BUNDLE; j++) {
+        const unsigned w0 = B.c[j].x;
+        double x = B.x[j], y = B.y[j];
+        if (w0 & TC_F_ALATE) x = tc_late(sm, B.c[j].y, tid8m1);
+        if (w0 & TC_F_BLATE) y = tc_late(sm, B.c[j].z, tid8m1);
+        if ((w0 & 0x7fu) == OP_MADD) {                    // acc = [acc] +- x*y   (a*b+c*d+... :1007-1029)
+            double t = __dmul_rn(x, y);
+            if (w0 & TC_F_NEGA) t = -t;
+            acc = (w0 & TC_F_FIRST) ? t : __dadd_rn(acc, t);
+        } else {
+            const double2 r = tc_cell_other(w0, acc, p, x, y);
+            acc = r.x;
+            p = r.y;
+        }
+        if (w0 & TC_F_END) {                              // warp-uniform
+            if (w0 & TC_F_NEG) acc = -acc;                // -(dot)               :1151-1164
+            sm[((w0 >> 16) & 0xffu) * TC_BLOCK + tid] = acc;
+            if ((w0 & TC_F_STORE) && pred) *(double *)(mb + B.c[j].w) = acc;
+        }
+    }
 }
 
 // Execute dependency group g for the lanes with pred set.  Must be called by all 32 lanes.
 __device__ __noinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_start, int g, bool pred) {
-    const uint4 *cells = c.tape + __ldg(group_start + g);
-    const int nb = (int)((__ldg(group_start + g + 1) - __ldg(group_start + g)) / TC_BUNDLE);
-    double *const mb = c.mb;
-    double *const ring = c.ring;
+    const uint32_t first = __ldg(group_start + g);
+    const uint4 *cells = c.tape + first;
+    const int nb = (int)((__ldg(group_start + g + 1) - first) / TC_BUNDLE);
+    char *const mb = (char *)c.mb;
+    double *const sm = c.sm;
+    const unsigned tid = threadIdx.x;
     double acc = 0.0, p = 0.0;
-
-    uint4 cn[TC_BUNDLE];          // next bundle: cells and operand values in flight
-    double xn[TC_BUNDLE], yn[TC_BUNDLE];
-#pragma unroll
-    for (int j = 0; j < TC_BUNDLE; j++) cn[j] = __ldg(cells + j);
-#pragma unroll
-    for (int j = 0; j < TC_BUNDLE; j++) {
-        xn[j] = tc_fetch(mb, cn[j].y, pred);
-        yn[j] = tc_fetch(mb, cn[j].z, pred);
-    }
-    for (int b = 0; b < nb; b++) {
-        uint4 cc[TC_BUNDLE];
-        double xc[TC_BUNDLE], yc[TC_BUNDLE];
-#pragma unroll
-        for (int j = 0; j < TC_BUNDLE; j++) {
-            cc[j] = cn[j];
-            xc[j] = xn[j];
-            yc[j] = yn[j];
-        }
-        if (b + 1 < nb) {         // warp-uniform: put the next bundle in flight before executing this one
-            const uint4 *nx = cells + (size_t)(b + 1) * TC_BUNDLE;
-#pragma unroll
-            for (int j = 0; j < TC_BUNDLE; j++) cn[j] = __ldg(nx + j);
-#pragma unroll
-            for (int j = 0; j < TC_BUNDLE; j++) {
-                xn[j] = tc_fetch(mb, cn[j].y, pred);
-                yn[j] = tc_fetch(mb, cn[j].z, pred);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < TC_BUNDLE; j++) {
-            const unsigned w0 = cc[j].x;
-            const unsigned op = w0 & 0xffu;
-            const double x = tc_late(c, ring, cc[j].y, xc[j]);
-            const double y = tc_late(c, ring, cc[j].z, yc[j]);
-            switch (op) {
-            case OP_NOP: break;
-            case OP_MADD: acc = __dadd_rn(acc, __dmul_rn(x, y)); break;            // a*b+c*d+...  :1007-1029
-            case OP_MSET: acc = __dmul_rn(x, y); break;
-            case OP_RSUBDIV: acc = __dadd_rn(x, -acc) / y; break;                  // (a0-(dot))/d :1081-1098
-            case OP_RSUB: acc = __dadd_rn(x, -acc); break;                         // a0-(dot)     :1128-1144
-            case OP_SUM2F:                                                         // +a-b+c...    :964-968
-                acc = __dadd_rn((w0 & TC_F_NEGA) ? -x : x, (w0 & TC_F_NEGB) ? -y : y);
-                break;
-            case OP_SUM2:
-                acc = __dadd_rn(__dadd_rn(acc, (w0 & TC_F_NEGA) ? -x : x), (w0 & TC_F_NEGB) ? -y : y);
-                break;
-            case OP_SUM1F: acc = (w0 & TC_F_NEGA) ? -x : x; break;
-            case OP_SUM1: acc = __dadd_rn(acc, (w0 & TC_F_NEGA) ? -x : x); break;
-            case OP_PSET: p = __dmul_rn(x, y); break;                              // products of >2 factors
-            case OP_PMUL1: p = __dmul_rn(p, x); break;
-            case OP_PMUL2: p = __dmul_rn(__dmul_rn(p, x), y); break;
-            case OP_P1SET: acc = __dmul_rn(p, x); break;
-            case OP_P1ADD: acc = __dadd_rn(acc, __dmul_rn(p, x)); break;
-            case OP_P2SET: acc = __dmul_rn(__dmul_rn(p, x), y); break;
-            case OP_P2ADD: acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(p, x), y)); break;
-            default: acc = tc_cell_slow(op, w0, acc, x, y); break;
-            }
-            if (w0 & TC_F_END) {                                                   // warp-uniform
-                if (w0 & TC_F_NEG) acc = -acc;                                     // -(dot)       :1151-1164
-                ring[((w0 >> 16) & 0xffu) * TC_BLOCK] = acc;
-                if ((w0 & TC_F_STORE) && pred) mb[(size_t)cc[j].w * TC_TILE] = acc;
-            }
+    tc_bundle B0, B1;              // double buffer: one bundle executes while the next is in flight
+    tc_fetch(B0, cells, mb, pred);
+    for (int b = 0; b < nb; b += 2) {
+        const bool more1 = b + 1 < nb, more2 = b + 2 < nb;    // warp-uniform
+        if (more1) tc_fetch(B1, cells + (size_t)(b + 1) * TC_BUNDLE, mb, pred);
+        tc_exec(B0, mb, sm, tid, pred, acc, p);
+        if (more1) {
+            if (more2) tc_fetch(B0, cells + (size_t)(b + 2) * TC_BUNDLE, mb, pred);
+            tc_exec(B1, mb, sm, tid, pred, acc, p);
         }
     }
 }

@@ -8,12 +8,18 @@ kernels in ``csrc/`` interpret with one instance per lane, so the same pre-built
 serves any problem structure.
 
 Tape = array of 128-bit CELLS.  A cell is one step of an accumulator machine with two
-registers per lane (``acc``, ``p``) and up to two memory operands::
+registers per lane (``acc``, ``p``) and two memory operands::
 
-    word 0   op (bits 0-7) | flags (bits 8-15) | ring slot of the result (bits 16-23)
-    word 1   operand A      bits 30-31 space (0 scratchbook slot, 1 constant pool, 2 result
-    word 2   operand B                        ring, 3 none), bits 0-29 index
-    word 3   scratchbook slot of the result (when F_STORE)
+    word 0   op (bits 0-6) | flags (bits 7-15) | ring slot of the result (bits 16-23)
+    word 1   operand A   early operand (scratchbook): byte offset slot*256 inside the warp's tile
+    word 2   operand B   late operand (F_ALATE/F_BLATE; shared memory): byte offset of the result-
+                         ring entry | 1 (the kernel adds thread*8), or of the constant-pool entry
+    word 3   byte offset slot*256 of the result in the scratchbook (when F_STORE)
+
+``op == OP_MADD`` is the hot path: ``acc = [acc] +- A*B`` (F_FIRST drops the old accumulator,
+F_NEGA negates the product); it covers sums of products of pairs, i.e. the dot products of the
+LDL factorisation, the triangular solves and the mat-vec products.  Every other cell kind goes
+through one out-of-line switch.
 
 An instruction of the reference ISA becomes 1..k cells; the LAST one
 carries F_END: the accumulator is the instruction's value, it is pushed into the per-lane
@@ -27,7 +33,8 @@ keep ~2*BUNDLE loads in flight per warp.  That is only legal for operands that a
 produced inside the look-ahead window: the lowering below redirects every operand whose
 producer is one of the previous ``RING`` results of the same group to the result ring, which
 covers the window (every instruction has at least one cell, and RING > 2*BUNDLE).  Values whose
-every use is served by the ring are never stored to the scratchbook at all.
+every use is served by the ring are never stored to the scratchbook at all.  Constants live in
+shared memory next to the ring.
 
 Image = 64 int64 header + 16 double header + sections (see ``serialize``).
 """
@@ -41,25 +48,29 @@ from . import itable as it
 from .csparse import CompiledProblem
 from .optimize import GeneratedSolver
 
-MAGIC = 0x3030324243540002  # "\x02\0TCB200" little-endian tag + format version
+MAGIC = 0x3030324243540003  # "\x03\0TCB200" little-endian tag + format version
 CONST_BIT = 1 << 30         # io[] words only (get/copy sources): constant-pool index
 NO_SLOT = 0xFFFFFFFF
 
-BUNDLE = 8                  # cells fetched/decoded together -- MUST match TC_BUNDLE in csrc/tc_vm.cuh
+BUNDLE = 4                  # cells fetched/decoded together -- MUST match TC_BUNDLE in csrc/tc_image.h
 RING = 32                   # results kept in the shared-memory ring -- MUST match TC_RING
+BLOCK = 128                 # threads per CTA -- MUST match TC_BLOCK
+MAX_CONSTS = 1024           # constant pool entries held in shared memory -- MUST match TC_MAXCONST
+TILE_BYTES = 256            # one scratchbook slot of one warp: 32 lanes x 8 bytes
+RING_BYTES = RING * BLOCK * 8
 
-SP_SLOT, SP_CONST, SP_RING, SP_NONE = 0, 1, 2, 3
-OPERAND_NONE = SP_NONE << 30
-
-F_STORE = 1 << 8            # write the result to scratchbook slot word3
-F_END = 1 << 9              # last cell of an instruction: push acc to the ring
-F_NEG = 1 << 10             # result = -acc
-F_NEGA = 1 << 11            # operand A enters with a minus sign (I_sum)
-F_NEGB = 1 << 12            # operand B enters with a minus sign (I_sum)
-F_INIT = 1 << 13            # min0/max0: acc=0 first; clp: acc=DBL_MAX first
+F_ALATE = 1 << 7            # operand A is read from shared memory at execution time
+F_BLATE = 1 << 8
+F_STORE = 1 << 9            # write the result to the scratchbook at byte offset word3
+F_END = 1 << 10             # last cell of an instruction: push acc to the ring
+F_NEG = 1 << 11             # result = -acc
+F_NEGA = 1 << 12            # operand A (OP_MADD: the product) enters with a minus sign
+F_NEGB = 1 << 13            # operand B enters with a minus sign (sums)
+F_INIT = 1 << 14            # min0/max0: acc=0 first; clp: acc=DBL_MAX first
+F_FIRST = 1 << 15           # OP_MADD: acc = +-A*B (no accumulation)
 
 # cell opcodes -- MUST match enum tc_cellop in csrc/tc_image.h
-(OP_NOP, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2, OP_MSET, OP_MADD, OP_PSET, OP_PMUL1, OP_PMUL2,
+(OP_MADD, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2, OP_NOP, OP_RESERVED, OP_PSET, OP_PMUL1, OP_PMUL2,
  OP_P1SET, OP_P1ADD, OP_P2SET, OP_P2ADD, OP_RSUB, OP_RSUBDIV, OP_NEGDIV, OP_DIV, OP_SQ1F, OP_SQ2F,
  OP_SQ1, OP_SQ2, OP_ABS1F, OP_ABS2F, OP_ABS1, OP_ABS2, OP_MINF1, OP_MINF2, OP_MIN1, OP_MIN2,
  OP_MAXF1, OP_MAXF2, OP_MAX1, OP_MAX2, OP_AMAXF1, OP_AMAXF2, OP_AMAX1, OP_AMAX2, OP_CLP, OP_PACC) = range(40)
@@ -88,19 +99,11 @@ def _mask128(groups) -> Tuple[int, int]:
     return lo, hi
 
 
-def _pairs_first_rest(ops: List[int], first_op: int, next_op: int) -> List[Tuple[int, int, int, int]]:
-    """cells (op, flags, A, B) for a left-to-right sum of products of PAIRS"""
-    cells = []
-    for k in range(0, len(ops), 2):
-        cells.append((first_op if k == 0 else next_op, 0, ops[k], ops[k + 1]))
-    return cells
-
-
 def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
-    """Cells [op, flags, A, B] of one instruction; ``opw`` are the encoded operand words in the
-    reference's operand order.  The arithmetic order is that of the emitted C statement
+    """Cells [op, flags, A, B] of one instruction; ``opw`` are operand tokens in the reference's
+    operand order (``None`` marks an unused operand).  The arithmetic order is that of the emitted C statement
     (instructionsTableUTHash.c:950-1539)."""
-    N = OPERAND_NONE
+    N = None
     c: List[List[int]] = []
 
     def two(xs, f1, f2, n1, n2, flags_first=0):
@@ -115,7 +118,7 @@ def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
 
     def dot(xs):
         for k in range(0, len(xs), 2):
-            c.append([OP_MSET if k == 0 else OP_MADD, 0, xs[k], xs[k + 1]])
+            c.append([OP_MADD, F_FIRST if k == 0 else 0, xs[k], xs[k + 1]])
 
     if t in (it.I_load, it.I_2):
         c.append([OP_SUM1F, 0, opw[0], N])
@@ -188,8 +191,8 @@ def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
 def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[str, np.ndarray]:
     pr: CompiledProblem = gen.problem
     tab, slot = pr.tab, pr.slot
-    if pr.n_slots >= CONST_BIT:
-        raise ValueError("scratchbook too large for the 30-bit slot field")
+    if pr.n_slots * TILE_BYTES >= 1 << 32:
+        raise ValueError("scratchbook too large for 32-bit tile offsets")
     if ring <= 2 * bundle:
         raise ValueError("the result ring must cover the operand look-ahead window (RING > 2*BUNDLE)")
     consts: List[float] = []
@@ -228,6 +231,18 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
     cells: List[List[int]] = []                 # [w0, w1, w2, w3]
     group_start = [0]
     stats = dict(slot_reads=0, ring_reads=0, const_reads=0, stores=0, ring_only=0)
+
+    def enc(tok, late_flag: int) -> Tuple[int, int]:
+        """operand token -> (word, flag)"""
+        if tok is None:                         # unused operand: a harmless shared-memory read
+            return RING_BYTES, late_flag
+        kind, v = tok
+        if kind == "slot":
+            return v * TILE_BYTES, 0
+        if kind == "ring":
+            return (v * BLOCK * 8) | 1, late_flag
+        return RING_BYTES + 8 * v, late_flag    # constant pool, stored right after the ring
+
     for members in pr.groups:
         order = {i: n for n, i in enumerate(members)}
         # furthest in-group consumer of every result, in results
@@ -240,7 +255,7 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
         for n, i in enumerate(members):
             t, p, ops = tab.types[i], tab.params[i], tab.operands[i]
             if t in (it.I_load, it.I_2):
-                opw = [(SP_CONST << 30) | cidx(const_of(i))]
+                opw = [("const", cidx(const_of(i)))]
                 stats["const_reads"] += 1
             else:
                 opw = []
@@ -248,25 +263,31 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
                     v = const_of(o)
                     k = order.get(o)
                     if v is not None:
-                        opw.append((SP_CONST << 30) | cidx(v))
+                        opw.append(("const", cidx(v)))
                         stats["const_reads"] += 1
                     elif k is not None and n - k < ring:
-                        opw.append((SP_RING << 30) | (k % ring))
+                        opw.append(("ring", k % ring))
                         stats["ring_reads"] += 1
                     else:
-                        opw.append((SP_SLOT << 30) | int(slot[o]))
+                        opw.append(("slot", int(slot[o])))
                         stats["slot_reads"] += 1
             cs = instruction_cells(t, p, opw)
             store = i in external or far.get(i, 0) >= ring
-            last = cs[-1]
-            last[1] |= F_STORE if store else 0
             stats["stores" if store else "ring_only"] += 1
-            for op, fl, a, b in cs[:-1]:
-                cells.append([op | fl, a, b, 0])
-            cells.append([last[0] | last[1] | ((n % ring) << 16), last[2], last[3], int(slot[i]) if store else 0])
+            for q, (op, fl, a, b_) in enumerate(cs):
+                wa, fa = enc(a, F_ALATE)
+                wb, fb = enc(b_, F_BLATE)
+                w0 = op | fl | fa | fb
+                w3 = 0
+                if q == len(cs) - 1:
+                    w0 |= ((n % ring) << 16) | (F_STORE if store else 0)
+                    w3 = int(slot[i]) * TILE_BYTES if store else 0
+                cells.append([w0, wa, wb, w3])
         while len(cells) % bundle:
-            cells.append([OP_NOP, OPERAND_NONE, OPERAND_NONE, 0])
+            cells.append([OP_NOP | F_ALATE | F_BLATE, RING_BYTES, RING_BYTES, 0])
         group_start.append(len(cells))
+    if len(consts) > MAX_CONSTS:
+        raise ValueError(f"{len(consts)} distinct constants exceed the shared-memory constant pool ({MAX_CONSTS})")
 
     # ---- function table ------------------------------------------------------------------------
     user_sets = [s for s in pr.sets.values() if s.kind in ("parameter", "variable")]

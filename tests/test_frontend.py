@@ -156,32 +156,35 @@ def test_memory_map_never_aliases_live_values():
 
 
 def test_tape_structure():
-    """groups start on bundle boundaries, every instruction ends in exactly one F_END cell, ring
-    operands always point at one of the previous RING results, look-ahead operands are never
-    produced inside the look-ahead window"""
+    """groups start on bundle boundaries, every instruction ends in exactly one F_END cell, late
+    operands point into the ring / constant pool, look-ahead operands are never produced inside
+    the look-ahead window"""
     from tenscalc_b200 import tape as tp
     gen, _ = generated("mpc_dcmotor")
     pr = gen.problem
     L = tp.lower(gen)
     cells, gs = L["tape"], L["group_start"]
     assert len(cells) % tp.BUNDLE == 0 and all(int(x) % tp.BUNDLE == 0 for x in gs)
+    assert tp.RING > 2 * tp.BUNDLE
     for g, members in enumerate(pr.groups):
         grp = cells[int(gs[g]):int(gs[g + 1])]
         ends = [k for k, c in enumerate(grp) if int(c[0]) & tp.F_END]
         assert len(ends) == len(members)
-        produced_at = {}                      # slot -> cell index of its store
+        produced_at = {}                      # scratchbook offset -> cell index of its store
         n = 0
         for k, c in enumerate(grp):
-            for w in (int(c[1]), int(c[2])):
-                if (w >> 30) == tp.SP_SLOT and w in produced_at:
-                    # fetched when the previous bundle starts executing
+            w0 = int(c[0])
+            for w, late in ((int(c[1]), w0 & tp.F_ALATE), (int(c[2]), w0 & tp.F_BLATE)):
+                if late:
+                    assert w < tp.RING_BYTES + 8 * tp.MAX_CONSTS
+                    continue
+                assert w % tp.TILE_BYTES == 0 and w // tp.TILE_BYTES < pr.n_slots
+                if w in produced_at:          # fetched when the previous bundle starts executing
                     fetch_time = (k // tp.BUNDLE - 1) * tp.BUNDLE
                     assert produced_at[w] < fetch_time, "look-ahead operand produced inside the window"
-                if (w >> 30) == tp.SP_RING:
-                    assert (w & 0xFF) < tp.RING
-            if int(c[0]) & tp.F_END:
-                assert ((int(c[0]) >> 16) & 0xFF) == n % tp.RING
-                if int(c[0]) & tp.F_STORE:
+            if w0 & tp.F_END:
+                assert ((w0 >> 16) & 0xFF) == n % tp.RING
+                if w0 & tp.F_STORE:
                     produced_at[int(c[3])] = k
                 n += 1
 
@@ -223,9 +226,18 @@ def _emulate_cells(L, g, m, consts, ring_size):
     def fetch(b):
         out = []
         for j in range(U):
-            c = cells[lo + b * U + j]
-            out.append([m[int(w) & 0x3FFFFFFF].copy() if (int(w) >> 30) == tp.SP_SLOT else None for w in (c[1], c[2])])
+            w0, wa, wb, _ = [int(v) for v in cells[lo + b * U + j]]
+            assert wa % 8 in (0, 1) and wb % 8 in (0, 1)
+            out.append([None if w0 & tp.F_ALATE else m[wa // tp.TILE_BYTES].copy(),
+                        None if w0 & tp.F_BLATE else m[wb // tp.TILE_BYTES].copy()])
         return out
+
+    def late(w):
+        if w & 1:
+            assert (w - 1) % (tp.BLOCK * 8) == 0 and w < tp.RING_BYTES
+            return ring[(w - 1) // (tp.BLOCK * 8)].copy()
+        assert w >= tp.RING_BYTES
+        return np.full(B, consts[(w - tp.RING_BYTES) // 8])
     nb = (hi - lo) // U
     nxt = fetch(0)
     with np.errstate(all="ignore"):
@@ -235,26 +247,22 @@ def _emulate_cells(L, g, m, consts, ring_size):
                 nxt = fetch(b + 1)
             for j in range(U):
                 w0, wa, wb, wr = [int(v) for v in cells[lo + b * U + j]]
-                op = w0 & 0xFF
-
-                def late(w, v):
-                    sp = w >> 30
-                    if sp == tp.SP_RING:
-                        return ring[w & 0xFF].copy()
-                    if sp == tp.SP_CONST:
-                        return np.full(B, consts[w & 0x3FFFFFFF])
-                    return v
-                x, y = late(wa, cur[j][0]), late(wb, cur[j][1])
-                sx = (lambda v: -v) if w0 & tp.F_NEGA else (lambda v: v)
-                sy = (lambda v: -v) if w0 & tp.F_NEGB else (lambda v: v)
+                op = w0 & 0x7F
+                x = late(wa) if w0 & tp.F_ALATE else cur[j][0]
+                y = late(wb) if w0 & tp.F_BLATE else cur[j][1]
+                sx = -x if w0 & tp.F_NEGA else x
+                sy = -y if w0 & tp.F_NEGB else y
                 init = bool(w0 & tp.F_INIT)
-                if op == tp.OP_NOP: pass
-                elif op == tp.OP_SUM1F: acc = sx(x)
-                elif op == tp.OP_SUM2F: acc = sx(x) + sy(y)
-                elif op == tp.OP_SUM1: acc = acc + sx(x)
-                elif op == tp.OP_SUM2: acc = (acc + sx(x)) + sy(y)
-                elif op == tp.OP_MSET: acc = x * y
-                elif op == tp.OP_MADD: acc = acc + x * y
+                if op == tp.OP_MADD:
+                    t = x * y
+                    if w0 & tp.F_NEGA:
+                        t = -t
+                    acc = t if w0 & tp.F_FIRST else acc + t
+                elif op == tp.OP_NOP: pass
+                elif op == tp.OP_SUM1F: acc = sx
+                elif op == tp.OP_SUM2F: acc = sx + sy
+                elif op == tp.OP_SUM1: acc = acc + sx
+                elif op == tp.OP_SUM2: acc = (acc + sx) + sy
                 elif op == tp.OP_PSET: p = x * y
                 elif op == tp.OP_PMUL1: p = p * x
                 elif op == tp.OP_PMUL2: p = (p * x) * y
@@ -302,7 +310,7 @@ def _emulate_cells(L, g, m, consts, ring_size):
                         acc = -acc
                     ring[(w0 >> 16) & 0xFF] = acc
                     if w0 & tp.F_STORE:
-                        m[wr] = acc
+                        m[wr // tp.TILE_BYTES] = acc
 
 
 @pytest.mark.parametrize("name", ["sls", "mpc_dcmotor", "mpc_quadcopter"])
