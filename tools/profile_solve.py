@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""One short batched solve for ncu captures (profiles/): `--max-iter` bounds the Newton
+iterations so that a full-occupancy launch replays in seconds.
+
+    ncu --set full --clock-control none --import-source on -k regex:tc_solve -c 1 \
+        -o gpurun_out/prof python tools/profile_solve.py --workload mpc_quadcopter --batch 75776 --max-iter 2
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="mpc_quadcopter")
+    ap.add_argument("--batch", type=int, default=75776)
+    ap.add_argument("--max-iter", type=int, default=2)
+    ap.add_argument("--repeat", type=int, default=1)
+    args = ap.parse_args()
+    from tenscalc_b200 import problems
+    gen, sargs = problems.BUILDERS[args.workload]()
+    P, V = problems.synthetic_inputs(args.workload, gen, args.batch, seed=7)
+    obj = gen(args.batch, device=0)
+    for n, _ in gen.parameters:
+        getattr(obj, "setP_" + n)(P[n])
+    for _ in range(args.repeat):
+        for n, _ in gen.variables:
+            getattr(obj, "setV_" + n)(V[n])
+        t = time.time()
+        st, it, sec = obj.solve(sargs["mu0"], args.max_iter or sargs["maxIter"], -1)
+        print(f"{args.workload} B={args.batch} maxIter={args.max_iter}: kernel {sec * 1e3:.1f} ms, "
+              f"wall {1e3 * (time.time() - t):.1f} ms, newton steps {int(it.sum())}, "
+              f"status histogram {dict(zip(*np.unique(st, return_counts=True)))}")
+    obj.close()
+
+
+if __name__ == "__main__":
+    main()
