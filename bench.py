@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per core in the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--backend", default="compiled", choices=["compiled", "tape"],
+                    help="compiled: per-problem sm_100a module (default); tape: generic interpreter")
     return ap.parse_args()
 
 
@@ -247,7 +249,8 @@ def run_ours(args, rank, local_rank, world):
     d_iter = torch.zeros(B, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
 
-    obj = gen(B, device=local_rank)
+    obj = gen(B, device=local_rank, backend=args.backend)
+    assert obj.has_module() == (args.backend == "compiled")
     ext = torch.cuda.ExternalStream(obj.stream_ptr(), device=torch.device("cuda", local_rank))
     mu0, maxIter = sargs["mu0"], sargs["maxIter"]
     d_out_ptrs = [t.data_ptr() for t in d_out]
@@ -328,7 +331,13 @@ def run_ours(args, rank, local_rank, world):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # rank-0 kernel: algorithmic bytes it executed per launch / its mean duration
         alg_bytes = float((counts * tables["boundary_bytes"]).sum()) / K
-        vm_bytes = float((counts * tables["vm_bytes"]).sum()) / K
+        if args.backend == "compiled":     # bytes the emitted code loads/stores (after per-chunk register reuse)
+            from tenscalc_b200.emit_cuda import emit_module
+            per_group = emit_module(gen)[1]["per_group"]
+            issued = np.array([8.0 * (g["loads"] + g["stores"]) for g in per_group])
+        else:
+            issued = tables["vm_bytes"]
+        vm_bytes = float((counts * issued).sum()) / K
         flops = float((counts * tables["flops"]).sum()) / K
         kms = float(np.mean(solve_ms))
         traffic = None
@@ -354,8 +363,8 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "kernel": "tc_solve_kernel", "kernel_ms": kms, "kernel_share_of_step": kms * K / total_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "vm_issued_bytes_per_launch": vm_bytes,
+                         "kernel": "tcm_solve_kernel" if args.backend == "compiled" else "tc_solve_kernel", "kernel_ms": kms, "kernel_share_of_step": kms * K / total_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "issued_bytes_per_launch": vm_bytes, "backend": args.backend,
                          "algorithmic_gflops": flops / (kms * 1e-3) / 1e9},
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {

@@ -34,6 +34,7 @@ typedef struct tc_solver tc_solver;
 #define TC_EINVAL  (-1)  /* bad argument (index, batch size, null pointer) */
 #define TC_EFORMAT (-2)  /* problem image not recognised                   */
 #define TC_ENOGPU  (-3)  /* no CUDA device: there is no CPU fallback       */
+#define TC_EMODULE (-4)  /* compiled problem module missing or mismatched  */
 
 /* Library / device queries. */
 int tc_version(void);
@@ -44,6 +45,16 @@ int tc_device_count(void);
  * handle owns all device memory; one CUDA stream per handle; handles are independent. */
 int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t batch, int device);
 int tc_destroy(tc_solver *s);
+
+/* Attach the per-problem COMPILED module: the shared object that tenscalc_b200.build.build_module
+ * produces from the sm_100a CUDA emitted for this problem (replaces the dynamic library that
+ * cmex2optimizeCS compiles from generated C, lib/cmex2optimizeCS.m:403-433, and that the reference's
+ * gateways dlopen per call, instructionsTableHeight4MEX.c:39-53).  After this call tc_solve* and
+ * tc_get_outputs* run the module's kernels (straight-line code of every dependency group as native
+ * SASS); without it they run the generic tape interpreter over the same image.  `fingerprint`
+ * (may be NULL) must match the instruction-list hash the module was generated from. */
+int tc_attach_module(tc_solver *s, const char *module_path, const char *fingerprint);
+int tc_has_module(const tc_solver *s);
 
 /* Introspection (what the generated class's help text lists). */
 int64_t tc_batch(const tc_solver *s);

@@ -39,3 +39,98 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
+
+
+# --------------------------------------------------------------------------------------------
+# per-problem compiled modules (the counterpart of the dynamic library cmex2optimizeCS builds
+# with the C compiler at generation time, lib/cmex2optimizeCS.m:403-433)
+# --------------------------------------------------------------------------------------------
+GEN_DIR = os.path.join(HERE, "_gen")
+MODULE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+                "-rdc=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", CSRC]
+
+
+def _toolchain_tag(emit_opts: dict) -> str:
+    """hash of everything besides the instruction list that shapes the module: the device headers,
+    the emitter, the compiler flags and the chunking options (content-based: mtimes do not survive
+    the copy to the GPU box)"""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cuh", ".h")):
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(HERE, "emit_cuda.py"), "rb").read())
+    h.update(repr((MODULE_FLAGS[:-1], sorted(emit_opts.items()))).encode())   # includes warps_per_sm -> -maxrregcount
+    return h.hexdigest()[:8]
+
+
+def module_path(gen, **emit_opts) -> str:
+    from .csparse import fingerprint
+    return os.path.join(GEN_DIR, f"{gen.classname}_{fingerprint(gen.problem)[:10]}_{_toolchain_tag(emit_opts)}.so")
+
+
+def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0, **emit_opts) -> str:
+    """Emit the CUDA module of a generated solver and compile it for sm_100a (in-tree, so the
+    .so travels to the GPU box).  Returns the path of the shared object."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    from .emit_cuda import emit_module
+    so = module_path(gen, **emit_opts)
+    if not force and os.path.exists(so):
+        return so
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        raise RuntimeError(f"compiled module {so} is missing and nvcc is not available to build it")
+    t0 = time.time()
+    files, stats = emit_module(gen, **emit_opts)
+    src_dir = os.path.join(GEN_DIR, "src", os.path.basename(so)[:-3])
+    cache_dir = os.path.join(GEN_DIR, "src", "objcache")     # part files do not depend on the launch shape
+    os.makedirs(src_dir, exist_ok=True)
+    os.makedirs(cache_dir, exist_ok=True)
+    for f in os.listdir(src_dir):
+        os.remove(os.path.join(src_dir, f))
+    for name, src in files.items():
+        with open(os.path.join(src_dir, name), "w") as f:
+            f.write(src)
+    import hashlib
+    import shutil
+
+    # register budget of the chunk functions: the kernel runs warps_per_sm warps on the 64K-register SM
+    reg_budget = min(255, 65536 // (32 * int(emit_opts.get("warps_per_sm", 8))) // 8 * 8)
+    flags = MODULE_FLAGS + [f"-maxrregcount={reg_budget}"]
+
+    def compile_one(name: str) -> str:
+        obj = os.path.join(src_dir, name[:-3] + ".o")
+        key = hashlib.sha1((files[name] + repr(flags[:-3]) + flags[-1]).encode()).hexdigest()
+        cached = os.path.join(cache_dir, key + ".o")
+        if name != "main.cu" and os.path.exists(cached):
+            shutil.copyfile(cached, obj)
+            return ""
+        res = subprocess.run([nvcc] + flags + ["-Xptxas", "-v", "-dc", os.path.join(src_dir, name), "-o", obj],
+                             capture_output=True, text=True)
+        if res.returncode:
+            raise RuntimeError(f"nvcc failed on {name}:\n{res.stdout}{res.stderr}")
+        if name != "main.cu":
+            shutil.copyfile(obj, cached)
+        return res.stderr
+
+    names = sorted(files, key=lambda n: -len(files[n]))
+    with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as pool:
+        logs = list(pool.map(compile_one, names))
+    objs = [os.path.join(src_dir, n[:-3] + ".o") for n in names]
+    res = subprocess.run([nvcc] + flags + ["-shared"] + objs + ["-o", so], capture_output=True, text=True)
+    if res.returncode:
+        raise RuntimeError(f"nvcc link failed:\n{res.stdout}{res.stderr}")
+    import re
+    text = "\n".join(logs)
+    regs = [int(x) for x in re.findall(r"Used (\d+) registers", text)]
+    spills = [int(a) for a in re.findall(r"(\d+) bytes spill stores", text)]
+    with open(os.path.join(src_dir, "build.log"), "w") as f:
+        f.write(f"emit+compile {time.time() - t0:.1f}s files {len(files)} functions {stats['n_functions']} "
+                f"max_regs {max(regs) if regs else 0} spill_store_bytes {sum(spills)} traffic {stats['total']}\n")
+        f.write(text)
+    if verbose:
+        print(f"module {os.path.basename(so)}: {time.time() - t0:.1f}s, {len(files)} files, "
+              f"{stats['n_functions']} functions, max regs {max(regs) if regs else 0}, "
+              f"spill stores {sum(spills)} B, {stats['total']}")
+    return so

@@ -3,61 +3,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <new>
 #include <vector>
 
 #include "../../include/tenscalc_b200.h"
-#include "tc_driver.cuh"
+#include "tc_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &P, int64_t inst) {
-    // result ring [slot][thread] (conflict-free), then the constant pool (broadcast reads)
-    __shared__ double sm[TC_RING_DOUBLES + TC_MAXCONST];
-    for (int k = threadIdx.x; k < P.n_consts; k += TC_BLOCK) sm[TC_RING_DOUBLES + k] = P.consts[k];
-    __syncthreads();
-    c.sm = sm;
-    c.mb = &TC_M(P, 0, inst);
-    c.consts = P.consts;
-    c.tape = P.tape;
-    c.lane = threadIdx.x & 31u;
-    c.st[0] = P.group_status[inst];
-    c.st[1] = P.group_status[P.stride + inst];
-}
-
-__device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device_image &P, int64_t inst) {
-    P.group_status[inst] = c.st[0];
-    P.group_status[P.stride + inst] = c.st[1];
-}
-
-// whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
-__global__ void __launch_bounds__(TC_BLOCK, 4) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
-                                                            double aeU, double aeEq,
-                                                            int32_t *__restrict__ status,
-                                                            int32_t *__restrict__ iter) {
-    const int64_t inst = (int64_t)blockIdx.x * TC_BLOCK + threadIdx.x;
-    const bool valid = inst < P.batch;
-    tc_lane c;
-    tc_lane_init(c, P, inst);
-    int st, it;
-    tc_ipm_solve(c, P, valid, mu0, maxIter, aeU, aeEq, st, it);
-    tc_lane_finish(c, P, inst);
-    if (valid) {
-        status[inst] = st;
-        iter[inst] = it;
-    }
-}
-
-// lazy evaluation of the parents of one get function (classname_getOutputs)
-__global__ void __launch_bounds__(TC_BLOCK, 4) tc_eval_kernel(tc_device_image P, int fn) {
-    const int64_t inst = (int64_t)blockIdx.x * TC_BLOCK + threadIdx.x;
-    tc_lane c;
-    tc_lane_init(c, P, inst);
-    tc_get(c, P, fn, inst < P.batch);
-    tc_lane_finish(c, P, inst);
-}
-
 // classname_set_<name>: values[batch][n] -> m[slot_k][instance]  (32x32 tiles through smem so
 // that both the read and the write are coalesced), then groupStatus[children]=0
 __global__ void tc_set_kernel(tc_device_image P, int fn, const double *__restrict__ values,
@@ -137,7 +92,13 @@ struct tc_solver {
     size_t stage_bytes = 0;
     int64_t n_slots = 0, launches = 0;
     float last_ms = 0.f;
+    // compiled back end: per-problem module (tenscalc_b200/emit_cuda.py), NULL = tape interpreter
+    void *module = nullptr;
+    int (*mod_solve)(const tc_device_image *, double, int, double, double, int32_t *, int32_t *, void *) = nullptr;
+    int (*mod_eval)(const tc_device_image *, int, void *) = nullptr;
 };
+
+#define TCM_ABI 1
 
 #define TC_CUDA(x)                           \
     do {                                     \
@@ -161,6 +122,7 @@ const char *tc_error_string(int code) {
     case TC_EINVAL: return "invalid argument";
     case TC_EFORMAT: return "unrecognised problem image";
     case TC_ENOGPU: return "no CUDA device (there is no CPU fallback)";
+    case TC_EMODULE: return "compiled problem module missing, unloadable or built for another problem/ABI";
     }
     return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
 }
@@ -185,7 +147,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     if (!s) return TC_EINVAL;
     s->device = device;
     s->batch = batch;
-    s->stride = (batch + TC_BLOCK - 1) / TC_BLOCK * TC_BLOCK;
+    s->stride = (batch + 255) / 256 * 256;   // whole CTAs for every back end (TC_BLOCK, 32*TC_LOCKSTEP <= 256)
     const int64_t n_slots = ih[1], n_groups = ih[2], n_funcs = ih[3], n_sets = ih[4], n_out = ih[5],
                   tape_cells = ih[6], n_consts = ih[7], io_words = ih[8];
     s->n_slots = n_slots;
@@ -279,9 +241,43 @@ int tc_destroy(tc_solver *s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->module) dlclose(s->module);
     delete s;
     return 0;
 }
+
+int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
+    if (!s || !path || s->module) return TC_EINVAL;
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        fprintf(stderr, "tenscalc_b200: %s\n", dlerror());
+        return TC_EMODULE;
+    }
+    auto abi = (int (*)(void))dlsym(h, "tcm_abi_version");
+    auto img = (int (*)(void))dlsym(h, "tcm_image_bytes");
+    auto blk = (int (*)(void))dlsym(h, "tcm_block");
+    auto fp = (const char *(*)(void))dlsym(h, "tcm_fingerprint");
+    auto solve = (decltype(s->mod_solve))dlsym(h, "tcm_solve");
+    auto eval = (decltype(s->mod_eval))dlsym(h, "tcm_eval");
+    auto load = (int (*)(void))dlsym(h, "tcm_load");
+    if (!load || !abi || !img || !blk || !fp || !solve || !eval || abi() != TCM_ABI || img() != (int)sizeof(tc_device_image) ||
+        blk() <= 0 || s->stride % blk() || (fingerprint && strcmp(fingerprint, fp()))) {
+        dlclose(h);
+        return TC_EMODULE;
+    }
+    cudaSetDevice(s->device);
+    int rc = load();
+    if (rc) {
+        dlclose(h);
+        return rc;
+    }
+    s->module = h;
+    s->mod_solve = solve;
+    s->mod_eval = eval;
+    return 0;
+}
+
+int tc_has_module(const tc_solver *s) { return s ? (s->module != nullptr) : TC_EINVAL; }
 
 int64_t tc_batch(const tc_solver *s) { return s ? s->batch : TC_EINVAL; }
 int tc_num_sets(const tc_solver *s) { return s ? (int)s->set_fids.size() : TC_EINVAL; }
@@ -326,10 +322,15 @@ int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, con
     (void)saveIter;   // allowSave is a code-generation-time option of the reference (cmex2optimizeCS.m:326)
     TC_CUDA(cudaSetDevice(s->device));
     TC_CUDA(cudaEventRecord(s->ev0, s->stream));
-    tc_solve_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(
-        s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter);
+    if (s->module) {
+        TC_CUDA((cudaError_t)s->mod_solve(&s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status,
+                                          d_iter, (void *)s->stream));
+    } else {
+        tc_solve_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(
+            s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter);
+        TC_CUDA(cudaGetLastError());
+    }
     s->launches++;
-    TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaEventRecord(s->ev1, s->stream));
     return 0;
 }
@@ -347,11 +348,17 @@ int tc_solve(tc_solver *s, const double *mu0, const int32_t *maxIter, const int3
     return 0;
 }
 
+static int tc_launch_eval(tc_solver *s, int fn) {
+    s->launches++;
+    if (s->module) return s->mod_eval(&s->img, fn, (void *)s->stream);
+    tc_eval_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(s->img, fn);
+    return (int)cudaGetLastError();
+}
+
 int tc_get_outputs_device(tc_solver *s, double *const *d_y) {
     if (!s || !d_y) return TC_EINVAL;
     TC_CUDA(cudaSetDevice(s->device));
-    tc_eval_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(s->img, (int)FN_getOutputs);
-    s->launches++;
+    TC_CUDA((cudaError_t)tc_launch_eval(s, (int)FN_getOutputs));
     for (size_t k = 0; k < s->out_sizes.size(); k++) {
         const uint32_t n = s->out_sizes[k];
         dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
@@ -364,8 +371,7 @@ int tc_get_outputs_device(tc_solver *s, double *const *d_y) {
 int tc_get_outputs(tc_solver *s, double *const *y) {
     if (!s || !y) return TC_EINVAL;
     TC_CUDA(cudaSetDevice(s->device));
-    tc_eval_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(s->img, (int)FN_getOutputs);
-    s->launches++;
+    TC_CUDA((cudaError_t)tc_launch_eval(s, (int)FN_getOutputs));
     for (size_t k = 0; k < s->out_sizes.size(); k++) {
         const uint32_t n = s->out_sizes[k];
         dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);

@@ -60,7 +60,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     }
     if (hasG) tc_copy(c, P, FN_initDualEqX, run);                           // :232-235
 
-    while (__any_sync(TC_FULL, run)) {                                      // :282
+    while (TC_ANY(run)) {                                      // :282
         if (run) iter++;
         if (run && iter > maxIter) { status = 8; run = false; }             // :308-313
 
@@ -160,7 +160,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             tc_set_scalar(c, P, FN_setAlphaPrimal, alphaPrimal, zero_now || ls != LS_DONE);
             zero_now = false;
             const bool ev = ls != LS_DONE;
-            if (!__any_sync(TC_FULL, ev)) break;
+            if (!TC_ANY(ev)) break;
             tc_get(c, P, FN_getMinF_s, ev);
             const double f = tc_value(c, P, FN_getMinF_s, 0, ev);
             if (ev) switch (ls) {
@@ -252,7 +252,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
 
     // ---- diagnostic bits when maxIter was reached (:885-920) ----
     const bool diag = valid && status == 8;
-    if (__any_sync(TC_FULL, diag)) {
+    if (TC_ANY(diag)) {
         tc_get(c, P, FN_getNorminf_Grad, diag);
         norminf_grad = tc_value(c, P, FN_getNorminf_Grad, 0, diag);
         if (diag && norminf_grad > D.gradTolerance) status |= 16;

@@ -27,6 +27,17 @@
 
 #define TC_FULL 0xFFFFFFFFu
 
+// Uniform control decisions.  By default a warp is autonomous and decides by warp vote.  With
+// TC_LOCKSTEP=W (compiled back end) the W warps of a CTA walk the driver and the chunk functions
+// TOGETHER (CTA-wide votes, one barrier per chunk), so that the instruction stream of the
+// straight-line code -- megabytes of SASS per Newton step, far beyond the instruction caches --
+// is fetched once per CTA instead of once per warp.
+#if defined(TC_LOCKSTEP) && TC_LOCKSTEP > 1
+#define TC_ANY(x) (__syncthreads_or((int)(x)) != 0)
+#else
+#define TC_ANY(x) (__any_sync(TC_FULL, (x)) != 0)
+#endif
+
 struct tc_lane {
     double *mb;            // &m[tile][0][lane]; slot k of this instance is mb[k*32]
     const double *consts;
@@ -36,6 +47,19 @@ struct tc_lane {
     uint64_t st[2];        // groupStatus[] of this instance, one bit per group
 };
 
+#ifdef TC_COMPILED_GROUPS
+// Compiled back end: the straight-line code of the groups and of the copy functions is CUDA C
+// generated per problem by tenscalc_b200/emit_cuda.py and linked into the same module.
+// run dependency group g on the instances with pred set; called by every thread that took the
+// vote (warp, or CTA under TC_LOCKSTEP: then every chunk ends in a CTA barrier)
+extern __device__ void tcm_group(int g, double *m, bool pred);
+extern __device__ bool tcm_copy(int fn, double *m);          // copy function fn; false: no compiled body
+
+__device__ __forceinline__ void tc_exec_group(tc_lane &c, const uint32_t *, int g, bool pred) {
+    tcm_group(g, c.mb, pred);
+    __syncwarp();
+}
+#else
 __device__ __forceinline__ double tc_unary(int op, double x) {
     switch (op) {   // C forms: instructionsTableUTHash.c:1347-1539
     case I_inv: return 1.0 / x;
@@ -205,6 +229,8 @@ __device__ __noinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_sta
     }
 }
 
+#endif  // TC_COMPILED_GROUPS
+
 // ---- lazy group evaluation and set/get/copy wrappers (writeCfunctionpergroup.m:513-852) ------
 // io[] word of a get/copy source: scratchbook slot, or constant-pool index when TC_CONST_BIT is set
 __device__ __forceinline__ double tc_ldop(const tc_lane &c, uint32_t w, bool pred) {
@@ -222,11 +248,11 @@ __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image
             bits &= bits - 1;
             bool need = pred && !((c.st[w] >> b) & 1ull);
             const unsigned vote = __ballot_sync(TC_FULL, need);
-            if (vote) {
+            if (TC_ANY(need)) {
                 tc_exec_group(c, P.group_start, 64 * w + b, need);
                 // static per-group flop/byte tables x these counts = algorithmic work (the
                 // reference's profiling counters, writeCfunctionpergroup.m:149-177,481-492)
-                if (c.lane == 0) atomicAdd(P.group_count + 64 * w + b, (unsigned long long)__popc(vote));
+                if (c.lane == 0 && vote) atomicAdd(P.group_count + 64 * w + b, (unsigned long long)__popc(vote));
             }
             if (need) c.st[w] |= 1ull << b;
         }
@@ -259,6 +285,17 @@ __device__ __forceinline__ double tc_value(const tc_lane &c, const tc_device_ima
 __device__ __noinline__ void tc_copy(tc_lane &c, const tc_device_image &P, int fn, bool pred) {
     const tc_func *f = P.funcs + fn;
     tc_run_parents(c, P, f, pred);
+#ifdef TC_COMPILED_GROUPS
+    {
+        bool done = true;
+        if (pred) done = tcm_copy(fn, c.mb);
+        __syncwarp();
+        if (__all_sync(TC_FULL, done)) {
+            tc_invalidate(c, f, pred);
+            return;
+        }
+    }
+#endif
     const uint32_t *io = P.io + f->io_off;
     const uint32_t cnt = f->io_cnt;
     for (uint32_t k = 0; k < cnt; k += 2) {

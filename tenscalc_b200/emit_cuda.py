@@ -1,0 +1,307 @@
+"""sm_100a CUDA emitter: the straight-line code of every dependency group as CUDA C.
+
+Counterpart of the reference's C emitter (``writeCinstructionsC``,
+``lib/csparse/instructionsTableUTHash.c:790-1609`` driven by
+``lib/@csparse/writeCfunctionpergroup.m:410-443``), re-designed for one-instance-per-lane
+execution on Blackwell:
+
+* every group becomes a sequence of CHUNK functions ``tcg<g>_<k>(double *m)``; ``m`` points at
+  the lane's column of the warp's scratchbook tile, so slot ``s`` of the instance is
+  ``m[32*s]`` and a warp-wide access is one contiguous 256-byte segment (``tc_image.h``);
+* inside a chunk every instruction result is a NAMED LOCAL (a register), every scratchbook
+  operand is loaded once per chunk, and a result is written back to the scratchbook only if
+  somebody outside the chunk reads it (another chunk, another group, a get or a copy) --
+  short-lived temporaries never touch HBM, and ptxas is free to hoist the independent loads
+  of a chunk far ahead of their uses (that is what hides HBM latency at one instance per lane);
+* constants are immediates;
+* the expression of every instruction is the C expression of the reference emitter,
+  evaluated in the same order; the translation units are compiled with ``-fmad=false`` so
+  multiplies and adds round separately like the reference's x86-64 build.
+
+The chunk size bounds both ptxas' compile time (which is super-linear in the size of a basic
+block) and the register pressure inside a chunk.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Set, Tuple
+
+from . import itable as it
+from .csparse import CompiledProblem
+
+TILE = 32                  # lanes per scratchbook tile -- MUST match TC_TILE
+MAX_TERMS = it.MAX_TERMS_PERLINE
+
+
+def _lit(v: float) -> str:
+    if v != v or v in (float("inf"), float("-inf")):
+        raise ValueError("non-finite constant")
+    return float(v).hex() if v != int(v) or abs(v) >= 1e15 else f"{int(v)}.0"
+
+
+def expression(t: int, p: Sequence[float], o: List[str], r: str) -> str:
+    """CUDA statements computing instruction (t,p) with operand expressions ``o`` into the
+    new local ``r``; forms and order of instructionsTableUTHash.c:950-1539."""
+
+    def pairs(xs: Sequence[str]) -> str:
+        return "+".join(f"{xs[k]}*{xs[k + 1]}" for k in range(0, len(xs), 2))
+
+    if t == it.I_sum:                                                         # :964-968
+        return f"const double {r}=" + "".join(("+" if s > 0 else "-") + x for s, x in zip(p, o)) + ";"
+    if t == it.I_sumprod:                                                     # :1007-1029
+        m = int(p[0])
+        if len(o) > MAX_TERMS:
+            raise NotImplementedError("sumprod with more than one emitted line")
+        return f"const double {r}=" + "+".join("*".join(o[k:k + m]) for k in range(0, len(o), m)) + ";"
+    if t == it.I_plus_minus_dot_div:                                          # :1081-1098
+        return f"const double {r}=({o[0]}-({pairs(o[2:])}))/{o[1]};"
+    if t == it.I_minus_dot_div:                                               # :1106-1121
+        return f"const double {r}=-({pairs(o[1:])})/{o[0]};"
+    if t == it.I_plus_minus_dot:                                              # :1128-1144
+        return f"const double {r}={o[0]}-({pairs(o[1:])});"
+    if t == it.I_minus_dot:                                                   # :1151-1164
+        return f"const double {r}=-({pairs(o)});"
+    if t == it.I_div:
+        return f"const double {r}={o[0]}/{o[1]};"
+    if t == it.I_plus_sqr:                                                    # :1201-1210
+        return f"const double {r}=" + "+".join(f"{x}*{x}" for x in o) + ";"
+    if t == it.I_plus_abs:                                                    # :1217-1225
+        return f"const double {r}=" + "+".join(f"fabs({x})" for x in o) + ";"
+    if t in (it.I_min, it.I_max):                                             # :1232-1243
+        c = ">" if t == it.I_min else "<"
+        return f"double {r}={o[0]};" + "".join(f" if ({r}{c}{x}) {r}={x};" for x in o[1:])
+    if t in (it.I_min0, it.I_max0):                                           # :1250-1259
+        c = ">" if t == it.I_min0 else "<"
+        return f"double {r}=0.0;" + "".join(f" if ({r}{c}{x}) {r}={x};" for x in o)
+    if t == it.I_max_abs:                                                     # :1301-1312
+        return f"double {r}=fabs({o[0]});" + "".join(f" if ({r}<fabs({x})) {r}=fabs({x});" for x in o[1:])
+    if t == it.I_clp:                                                         # :1318-1330
+        s = f"double {r}=DBL_MAX;"
+        for k in range(0, len(o), 2):
+            s += f" if ({o[k + 1]}<0) {{const double x_=-{o[k]}/{o[k + 1]}; if ({r}>x_) {r}=x_;}}"
+        return s
+    x = o[0] if o else ""
+    unary = {                                                                 # :1347-1539
+        it.I_round: f"round({x})", it.I_ceil: f"ceil({x})", it.I_floor: f"floor({x})",
+        it.I_abs: f"fabs({x})", it.I_sign: f"({x}>=0)?1.0:-1.0", it.I_2times: f"2.0*{x}",
+        it.I_6times: f"6.0*{x}", it.I_sqr: f"{x}*{x}", it.I_3sqr: f"3.0*{x}*{x}", it.I_cube: f"{x}*{x}*{x}",
+        it.I_sqrt: f"sqrt({x})", it.I_Dsqrt: f".5*pow({x},-.5)", it.I_DDsqrt: f"-.25*pow({x},-1.5)",
+        it.I_inv: f"1.0/{x}", it.I_minus_inv_sqr: f"-1.0/({x}*{x})", it.I_2_inv_cube: f"2.0/({x}*{x}*{x})",
+        it.I_cos: f"cos({x})", it.I_minus_cos: f"-cos({x})", it.I_sin: f"sin({x})",
+        it.I_minus_sin: f"-sin({x})", it.I_log: f"log({x})", it.I_exp: f"exp({x})", it.I_atan: f"atan({x})",
+        it.I_Datan: f"1.0/(1.0+{x}*{x})", it.I_DDatan: f"-2.0*{x}/(1.0+{x}*{x})/(1.0+{x}*{x})",
+        it.I_srelu: f"log(1.0+exp({x}))", it.I_dsrelu: f"1.0/(1.0+exp(-{x}))",
+        it.I_ddsrelu: f"1.0/(2.0+exp(-{x})+exp({x}))", it.I_relu: f"({x}>0)?{x}:0.0",
+        it.I_heaviside: f"({x}>0)?1.0:0.0",
+    }
+    if t in unary:
+        return f"const double {r}={unary[t]};"
+    raise NotImplementedError(it.OPNAMES.get(t, str(t)))
+
+
+def external_values(pr: CompiledProblem) -> Set[int]:
+    """values that must reach the scratchbook whatever the chunking: read by another group, a
+    get or a copy"""
+    tab = pr.tab
+    ext: Set[int] = set()
+    for g in pr.gets.values():
+        ext.update(x for s in g.sources for x in s if x is not None)
+    for c in pr.copies.values():
+        ext.update(c.src)
+    for i, gi in pr.group_of.items():
+        for o in tab.operands[i]:
+            if pr.group_of.get(o, -1) != gi:
+                ext.add(o)
+    return ext
+
+
+def chunk_group(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_loads: int) -> List[List[int]]:
+    """split a group into chunks: at most ``max_refs`` operand references and at most ``max_loads``
+    distinct scratchbook operands per chunk (they are all loaded up front and stay in registers)"""
+    tab = pr.tab
+    chunks: List[List[int]] = []
+    cur: List[int] = []
+    refs = 0
+    loaded: Set[int] = set()
+    made: Set[int] = set()
+    for i in members:
+        ops = [o for o in tab.operands[i] if tab.types[o] not in (it.I_load, it.I_2)]
+        new = {o for o in ops if o not in loaded and o not in made}
+        if cur and (refs + len(ops) > max_refs or len(loaded) + len(new) > max_loads):
+            chunks.append(cur)
+            cur, refs, loaded, made = [], 0, set(), set()
+            new = set(ops)
+        cur.append(i)
+        refs += len(ops)
+        loaded |= new
+        made.add(i)
+    if cur:
+        chunks.append(cur)
+    return chunks
+
+
+def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
+               max_loads: int = 96) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+    """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics"""
+    tab, slot = pr.tab, pr.slot
+    members = pr.groups[g]
+    chunks = chunk_group(pr, members, max_refs, max_loads)
+    chunk_of = {i: k for k, ch in enumerate(chunks) for i in ch}
+    # results read by a later chunk of the same group
+    cross: Set[int] = set()
+    for i in members:
+        for o in tab.operands[i]:
+            k = chunk_of.get(o)
+            if k is not None and k != chunk_of[i]:
+                cross.add(o)
+    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0)
+    out: List[Tuple[str, str]] = []
+    for k, ch in enumerate(chunks):
+        name = f"tcg{g}_{k}"
+        head = [f"__device__ __noinline__ void {name}(double *__restrict__ m) {{"]
+        loads: List[str] = []      # every scratchbook operand of the chunk, issued back to back up front:
+        lines: List[str] = []      # one memory round trip per chunk instead of one per use
+        have: Set[int] = set()
+        for i in ch:
+            t, p = tab.types[i], tab.params[i]
+            if t == it.I_set:
+                continue
+            if t in (it.I_load, it.I_2):      # constants are immediates at their uses (gets/copies read the pool)
+                continue
+            o: List[str] = []
+            for q in tab.operands[i]:
+                tq = tab.types[q]
+                if tq == it.I_load:
+                    o.append("(" + _lit(tab.params[q][0]) + ")")
+                elif tq == it.I_2:
+                    o.append("2.0")
+                else:
+                    if q not in have:
+                        loads.append(f"const double v{q}=m[{int(slot[q]) * TILE}];")
+                        have.add(q)
+                        stats["loads"] += 1
+                    else:
+                        stats["reg_reads"] += 1
+                    o.append(f"v{q}")
+            lines.append(expression(t, p, o, f"v{i}"))
+            have.add(i)
+            if i in ext or i in cross:
+                lines.append(f"m[{int(slot[i]) * TILE}]=v{i};")
+                stats["stores"] += 1
+            else:
+                stats["reg_only"] += 1
+        lines = head + loads + lines
+        lines.append("}")
+        out.append((name, "\n".join(lines) + "\n"))
+    return out, stats
+
+
+# --------------------------------------------------------------------------------------------
+# per-problem module: chunk functions spread over part files + main.cu (dispatch, kernels, ABI)
+# --------------------------------------------------------------------------------------------
+EMITTER_VERSION = 1
+TCM_ABI = 1
+
+
+def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) -> List[Tuple[str, str]]:
+    """chunks of one copy function: sequential ``m[d]=m[s]`` (writeCfunctionpergroup.m:753-852)"""
+    tab, slot = pr.tab, pr.slot
+    c = pr.copies[name]
+    pairs = [(d, s) for d, s in zip(c.dest, c.src) if d != s]
+    out = []
+    for k in range(0, max(len(pairs), 1), max_pairs):
+        lines = [f"__device__ __noinline__ void tcc{fn_id}_{k // max_pairs}(double *__restrict__ m) {{"]
+        for d, s in pairs[k:k + max_pairs]:
+            ts = tab.types[s]
+            if ts == it.I_load:
+                src = _lit(tab.params[s][0])
+            elif ts == it.I_2:
+                src = "2.0"
+            else:
+                src = f"m[{int(slot[s]) * TILE}]"
+            lines.append(f"m[{int(slot[d]) * TILE}]={src};")
+        lines.append("}")
+        out.append((f"tcc{fn_id}_{k // max_pairs}", "\n".join(lines) + "\n"))
+    return out
+
+
+def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
+                warps_per_sm: int = 8):
+    """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
+    from .csparse import fingerprint
+    from .tape import FN
+    pr: CompiledProblem = gen.problem
+    ext = external_values(pr)
+    funcs: List[Tuple[str, str]] = []
+    group_calls: List[List[str]] = []
+    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0)
+    per_group = []
+    for g in range(len(pr.groups)):
+        fs, st = emit_group(pr, g, ext, max_refs, max_loads)
+        funcs += fs
+        group_calls.append([n for n, _ in fs])
+        per_group.append(st)
+        for k in total:
+            total[k] += st[k]
+    copy_calls: Dict[int, List[str]] = {}
+    for name, fid in FN.items():
+        if name in pr.copies:
+            fs = emit_copy(pr, fid, name)
+            funcs += fs
+            copy_calls[fid] = [n for n, _ in fs]
+    # part files of roughly equal size (ptxas time is what we balance)
+    head = "// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n"
+    files: Dict[str, str] = {}
+    cur, size = [head], 0
+    for _, src in funcs:
+        if size and size + len(src) > part_bytes:
+            files[f"part_{len(files):03d}.cu"] = "".join(cur)
+            cur, size = [head], 0
+        cur.append(src)
+        size += len(src)
+    files[f"part_{len(files):03d}.cu"] = "".join(cur)
+    fp = fingerprint(pr)
+    if lockstep not in (1, 2, 4, 8):
+        raise ValueError("lockstep must be 1, 2, 4 or 8 warps per CTA")
+    if warps_per_sm % lockstep or not 1 <= warps_per_sm <= 32:
+        raise ValueError("warps_per_sm must be a multiple of lockstep, at most 32")
+    m = [head, f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n"
+               f"#define TC_KMINBLOCKS {warps_per_sm // lockstep}\n"]
+    m += [f"__device__ void {n}(double *__restrict__ m);\n" for n, _ in funcs]
+    m.append("__device__ __noinline__ void tcm_group(int g, double *m, bool p) {\n    switch (g) {\n")
+    bar = " __syncthreads();" if lockstep > 1 else ""
+    for g, calls in enumerate(group_calls):
+        m.append(f"    case {g}:" + "".join(f" if (p) {n}(m);{bar}" for n in calls) + " break;\n")
+    m.append("    }\n}\n")
+    m.append("__device__ __noinline__ bool tcm_copy(int fn, double *m) {\n    switch (fn) {\n")
+    for fid, calls in copy_calls.items():
+        m.append(f"    case {fid}: " + " ".join(f"{n}(m);" for n in calls) + " return true;\n")
+    m.append("    }\n    return false;\n}\n")
+    m.append(f'''#include "tc_kernels.cuh"
+extern "C" {{
+__attribute__((visibility("default"))) int tcm_abi_version(void) {{ return {TCM_ABI}; }}
+__attribute__((visibility("default"))) const char *tcm_fingerprint(void) {{ return "{fp}"; }}
+__attribute__((visibility("default"))) int tcm_image_bytes(void) {{ return (int)sizeof(tc_device_image); }}
+__attribute__((visibility("default"))) int tcm_block(void) {{ return TC_KBLOCK; }}
+// force the (lazy) load of the module's device code now rather than inside the first timed solve
+__attribute__((visibility("default"))) int tcm_load(void) {{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, tc_solve_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, tc_eval_kernel);
+    return (int)e;
+}}
+// ipmPD_CSsolver() for every instance of the batch: ONE launch, the Newton loop stays on the device
+__attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, double mu0, int maxIter, double aeU,
+                                                     double aeEq, int32_t *status, int32_t *iter, void *stream) {{
+    tc_solve_kernel<<<(unsigned)(P->stride / TC_KBLOCK), TC_KBLOCK, 0, (cudaStream_t)stream>>>(
+        *P, mu0, maxIter, aeU, aeEq, status, iter);
+    return (int)cudaGetLastError();
+}}
+// lazy evaluation of the parents of get function fn (classname_getOutputs)
+__attribute__((visibility("default"))) int tcm_eval(const tc_device_image *P, int fn, void *stream) {{
+    tc_eval_kernel<<<(unsigned)(P->stride / TC_KBLOCK), TC_KBLOCK, 0, (cudaStream_t)stream>>>(*P, fn);
+    return (int)cudaGetLastError();
+}}
+}}
+''')
+    files["main.cu"] = "".join(m)
+    return files, dict(total=total, per_group=per_group, n_functions=len(funcs), fingerprint=fp)

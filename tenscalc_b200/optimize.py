@@ -38,9 +38,9 @@ class GeneratedSolver:
     defines: Dict[str, object]
     info: Dict[str, object] = field(default_factory=dict)
 
-    def __call__(self, batch: int = 1, device: Optional[int] = None):
+    def __call__(self, batch: int = 1, device: Optional[int] = None, backend: str = "compiled", **module_opts):
         from .runtime import BatchedSolver
-        return BatchedSolver(self, batch, device)
+        return BatchedSolver(self, batch, device, backend, **module_opts)
 
 
 def _name_of(v: Tcalculus) -> str:

@@ -30,6 +30,8 @@ ABI = [
     ("tc_create", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_size_t,
                                  ctypes.c_int64, ctypes.c_int]),
     ("tc_destroy", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_attach_module", ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]),
+    ("tc_has_module", ctypes.c_int, [ctypes.c_void_p]),
     ("tc_batch", ctypes.c_int64, [ctypes.c_void_p]),
     ("tc_num_sets", ctypes.c_int, [ctypes.c_void_p]),
     ("tc_num_outputs", ctypes.c_int, [ctypes.c_void_p]),
@@ -103,7 +105,16 @@ def _check(rc: int) -> None:
 
 
 class BatchedSolver:
-    def __init__(self, gen: GeneratedSolver, batch: int, device: Optional[int] = None):
+    def __init__(self, gen: GeneratedSolver, batch: int, device: Optional[int] = None,
+                 backend: str = "compiled", **module_opts):
+        """``backend="compiled"`` (default) runs the per-problem sm_100a module that
+        :func:`tenscalc_b200.build.build_module` emits and compiles (built on first use when it is
+        not in ``tenscalc_b200/_gen/``, like cmex2optimizeCS compiles its C at generation time);
+        ``backend="tape"`` runs the generic tape interpreter (no per-problem compilation).
+        ``module_opts`` are emitter options (``lockstep``, ``max_refs``, ``max_live``), see
+        :func:`tenscalc_b200.emit_cuda.emit_module`."""
+        if backend not in ("compiled", "tape"):
+            raise ValueError("backend must be 'compiled' or 'tape'")
         lib = load_library()
         if lib.tc_device_count() == 0:
             raise TenscalcError("no CUDA device visible: the batched solver has no CPU path")
@@ -116,6 +127,17 @@ class BatchedSolver:
         _check(lib.tc_create(ctypes.byref(h), buf, len(self._image), self.batch, self.device))
         self._h = h
         self._lib = lib
+        self.backend = backend
+        if backend == "compiled":
+            from .build import build_module
+            from .csparse import fingerprint
+            try:
+                so = build_module(gen, **module_opts)
+                _check(lib.tc_attach_module(h, so.encode(), fingerprint(gen.problem).encode()))
+            except Exception:
+                lib.tc_destroy(h)
+                self._h = None
+                raise
         self._set_index: Dict[str, int] = {}
         for k, (n, _) in enumerate(gen.parameters):
             self._set_index["P_" + n] = k
@@ -246,6 +268,10 @@ class BatchedSolver:
         c = ctypes.c_int64(0)
         _check(self._lib.tc_total_newton_steps(self._h, ctypes.byref(c)))
         return c.value
+
+    def has_module(self) -> bool:
+        """True when the per-problem compiled module is attached (native SASS for every group)"""
+        return bool(self._lib.tc_has_module(self._h))
 
     def scratch_bytes(self) -> int:
         return int(self._lib.tc_scratch_bytes(self._h))

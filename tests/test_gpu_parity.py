@@ -21,12 +21,14 @@ def _oracle(gen, name):
     return Oracle(gen, "ref")
 
 
+@pytest.mark.parametrize("backend", ["compiled", "tape"])
 @pytest.mark.parametrize("name,batch,kw", CASES)
-def test_parity_with_oracle(name, batch, kw):
+def test_parity_with_oracle(name, batch, kw, backend):
     gen, args = generated(name, **kw)
     P, V = problems.synthetic_inputs(name, gen, batch, seed=1)
     st_o, it_o, out_o, _ = _oracle(gen, name).solve_batch(P, V, args["mu0"], args["maxIter"])
-    obj = gen(batch)
+    obj = gen(batch, backend=backend)
+    assert obj.has_module() == (backend == "compiled")
     for n, _ in gen.parameters:
         getattr(obj, "setP_" + n)(P[n])
     for n, _ in gen.variables:
@@ -44,5 +46,5 @@ def test_parity_with_oracle(name, batch, kw):
         a, b = outs[k][..., ok], out_o[k][..., ok]
         scale = np.maximum(np.abs(b).max(axis=tuple(range(b.ndim - 1)), keepdims=True), 1e-300)
         assert np.max(np.abs(a - b) / scale) <= 1e-8, k
-    print(f"{name}: B={batch} iters {it.min()}..{it.max()} equal_iters={np.array_equal(it, it_o)} "
+    print(f"{name}[{backend}]: B={batch} iters {it.min()}..{it.max()} equal_iters={np.array_equal(it, it_o)} "
           f"batch time {t * 1e3:.2f} ms")

@@ -21,11 +21,17 @@ def main():
     ap.add_argument("--batch", type=int, default=75776)
     ap.add_argument("--max-iter", type=int, default=2)
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--backend", default="compiled", choices=["compiled", "tape"])
+    ap.add_argument("--lockstep", type=int, default=0, help="warps per CTA walking the code together (0: default)")
+    ap.add_argument("--max-loads", type=int, default=0, help="scratchbook operands per chunk (0: default)")
+    ap.add_argument("--warps-per-sm", type=int, default=0, help="resident warps per SM = register budget (0: default)")
     args = ap.parse_args()
     from tenscalc_b200 import problems
     gen, sargs = problems.BUILDERS[args.workload]()
     P, V = problems.synthetic_inputs(args.workload, gen, args.batch, seed=7)
-    obj = gen(args.batch, device=0)
+    opts = {k: v for k, v in dict(lockstep=args.lockstep, max_loads=args.max_loads,
+                                      warps_per_sm=args.warps_per_sm).items() if v}
+    obj = gen(args.batch, device=0, backend=args.backend, **opts)
     for n, _ in gen.parameters:
         getattr(obj, "setP_" + n)(P[n])
     for _ in range(args.repeat):
@@ -33,9 +39,11 @@ def main():
             getattr(obj, "setV_" + n)(V[n])
         t = time.time()
         st, it, sec = obj.solve(sargs["mu0"], args.max_iter or sargs["maxIter"], -1)
-        print(f"{args.workload} B={args.batch} maxIter={args.max_iter}: kernel {sec * 1e3:.1f} ms, "
+        print(f"{args.workload}[{args.backend} {opts}] B={args.batch} maxIter={args.max_iter}: kernel {sec * 1e3:.1f} ms, "
               f"wall {1e3 * (time.time() - t):.1f} ms, newton steps {int(it.sum())}, "
-              f"status histogram {dict(zip(*np.unique(st, return_counts=True)))}")
+              f"status histogram {dict(zip(*np.unique(st, return_counts=True)))}, iter percentiles "
+              f"50/90/99/99.9/max {[int(x) for x in np.percentile(it, [50, 90, 99, 99.9, 100])]}, "
+              f"mean warp-max {it[:len(it) // 32 * 32].reshape(-1, 32).max(1).mean():.1f}")
     obj.close()
 
 
