@@ -77,6 +77,12 @@ int tc_solve(tc_solver *s, const double *mu0, const int32_t *maxIter, const int3
              const double *addEye2Hessian, int32_t *status, int32_t *iter, double *time);
 int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
                     const double *addEye2Hessian, int32_t *d_status, int32_t *d_iter);
+/* tc_solve without the final host synchronisation: the solve and the copies of status/iter into the
+ * (pinned) host arrays are only enqueued on the handle's stream; they are complete after the next
+ * tc_get_outputs or tc_synchronize on this handle.  Lets a caller keep several handles in flight so
+ * that the straggler tail of one batch overlaps the bulk of the next (bench.py --pipeline). */
+int tc_solve_async(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+                   const double *addEye2Hessian, int32_t *status, int32_t *iter);
 
 /* <class>_getOutputs: y[k] is double[batch][tc_output_size(k)], caller-allocated. */
 int tc_get_outputs(tc_solver *s, double *const *y);

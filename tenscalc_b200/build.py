@@ -45,7 +45,8 @@ if __name__ == "__main__":
 # per-problem compiled modules (the counterpart of the dynamic library cmex2optimizeCS builds
 # with the C compiler at generation time, lib/cmex2optimizeCS.m:403-433)
 # --------------------------------------------------------------------------------------------
-GEN_DIR = os.path.join(HERE, "_gen")
+GEN_DIR = os.path.join(HERE, "_gen")                                  # the modules (.so): travel to the GPU box
+GEN_SRC = os.path.join(os.path.dirname(HERE), "build", "gen_src")    # emitted CUDA + objects: stay here
 MODULE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
                 "-rdc=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", CSRC]
 
@@ -83,10 +84,11 @@ def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0,
         raise RuntimeError(f"compiled module {so} is missing and nvcc is not available to build it")
     t0 = time.time()
     files, stats = emit_module(gen, **emit_opts)
-    src_dir = os.path.join(GEN_DIR, "src", os.path.basename(so)[:-3])
-    cache_dir = os.path.join(GEN_DIR, "src", "objcache")     # part files do not depend on the launch shape
+    src_dir = os.path.join(GEN_SRC, os.path.basename(so)[:-3])
+    cache_dir = os.path.join(GEN_SRC, "objcache")     # part files do not depend on the launch shape
     os.makedirs(src_dir, exist_ok=True)
     os.makedirs(cache_dir, exist_ok=True)
+    os.makedirs(GEN_DIR, exist_ok=True)
     for f in os.listdir(src_dir):
         os.remove(os.path.join(src_dir, f))
     for name, src in files.items():

@@ -335,6 +335,16 @@ int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, con
     return 0;
 }
 
+int tc_solve_async(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+                   const double *addEye2Hessian, int32_t *status, int32_t *iter) {
+    if (!s || !status || !iter) return TC_EINVAL;
+    int rc = tc_solve_device(s, mu0, maxIter, saveIter, addEye2Hessian, s->d_status, s->d_iter);
+    if (rc) return rc;
+    TC_CUDA(cudaMemcpyAsync(status, s->d_status, s->batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    TC_CUDA(cudaMemcpyAsync(iter, s->d_iter, s->batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
 int tc_solve(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
              const double *addEye2Hessian, int32_t *status, int32_t *iter, double *time) {
     if (!s || !status || !iter) return TC_EINVAL;

@@ -53,15 +53,15 @@ def expression(t: int, p: Sequence[float], o: List[str], r: str) -> str:
             raise NotImplementedError("sumprod with more than one emitted line")
         return f"const double {r}=" + "+".join("*".join(o[k:k + m]) for k in range(0, len(o), m)) + ";"
     if t == it.I_plus_minus_dot_div:                                          # :1081-1098
-        return f"const double {r}=({o[0]}-({pairs(o[2:])}))/{o[1]};"
+        return f"const double {r}=TC_DIV(({o[0]}-({pairs(o[2:])})),{o[1]});"
     if t == it.I_minus_dot_div:                                               # :1106-1121
-        return f"const double {r}=-({pairs(o[1:])})/{o[0]};"
+        return f"const double {r}=TC_DIV(-({pairs(o[1:])}),{o[0]});"
     if t == it.I_plus_minus_dot:                                              # :1128-1144
         return f"const double {r}={o[0]}-({pairs(o[1:])});"
     if t == it.I_minus_dot:                                                   # :1151-1164
         return f"const double {r}=-({pairs(o)});"
     if t == it.I_div:
-        return f"const double {r}={o[0]}/{o[1]};"
+        return f"const double {r}=TC_DIV({o[0]},{o[1]});"
     if t == it.I_plus_sqr:                                                    # :1201-1210
         return f"const double {r}=" + "+".join(f"{x}*{x}" for x in o) + ";"
     if t == it.I_plus_abs:                                                    # :1217-1225
@@ -140,7 +140,7 @@ def chunk_group(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_
 
 
 def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
-               max_loads: int = 96) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+               max_loads: int = 96, prefetch: int = 1, merge: int = 1) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
     """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics"""
     tab, slot = pr.tab, pr.slot
     members = pr.groups[g]
@@ -153,13 +153,13 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             k = chunk_of.get(o)
             if k is not None and k != chunk_of[i]:
                 cross.add(o)
-    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0)
-    out: List[Tuple[str, str]] = []
+    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0)
+    bodies = []                    # per chunk: (name, load slots in issue order, store slots, statements)
     for k, ch in enumerate(chunks):
         name = f"tcg{g}_{k}"
-        head = [f"__device__ __noinline__ void {name}(double *__restrict__ m) {{"]
-        loads: List[str] = []      # every scratchbook operand of the chunk, issued back to back up front:
+        loads: List[int] = []      # every scratchbook operand of the chunk, issued back to back up front:
         lines: List[str] = []      # one memory round trip per chunk instead of one per use
+        stores: Set[int] = set()
         have: Set[int] = set()
         for i in ch:
             t, p = tab.types[i], tab.params[i]
@@ -176,7 +176,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                     o.append("2.0")
                 else:
                     if q not in have:
-                        loads.append(f"const double v{q}=m[{int(slot[q]) * TILE}];")
+                        loads.append(q)
                         have.add(q)
                         stats["loads"] += 1
                     else:
@@ -186,12 +186,34 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             have.add(i)
             if i in ext or i in cross:
                 lines.append(f"m[{int(slot[i]) * TILE}]=v{i};")
+                stores.add(int(slot[i]))
                 stats["stores"] += 1
             else:
                 stats["reg_only"] += 1
-        lines = head + loads + lines
-        lines.append("}")
-        out.append((name, "\n".join(lines) + "\n"))
+        bodies.append((name, loads, stores, lines))
+    out: List[Tuple[str, str]] = []
+    # `merge` consecutive chunks share one function (each chunk in its own scope): the ABI's
+    # callee-saved register spill/restore is paid once per function instead of once per chunk
+    for f0 in range(0, len(bodies), merge):
+        fname = bodies[f0][0]
+        src = [f"__device__ __noinline__ void {fname}(double *__restrict__ m) {{"]
+        for k in range(f0, min(f0 + merge, len(bodies))):
+            name, loads, stores, lines = bodies[k]
+            src.append("{")
+            src += [f"const double v{q}=m[{int(slot[q]) * TILE}];" for q in loads]
+            if prefetch and k + 1 < len(bodies):
+                # while this chunk's operands are in flight, pull the NEXT chunk's operands into L2: its
+                # load phase then costs an L2 hit instead of an HBM round trip (no registers involved)
+                mine = {int(slot[q]) for q in loads} | stores
+                nxt = [int(slot[q]) for q in bodies[k + 1][1] if int(slot[q]) not in mine]
+                if nxt:            # the clobber keeps this chunk's own loads ahead of the prefetches
+                    src.append('asm volatile("" ::: "memory");')
+                src += [f"TC_PREFETCH(m+{sl * TILE});" for sl in nxt]
+                stats["prefetches"] += len(nxt)
+            src += lines
+            src.append("}")
+        src.append("}")
+        out.append((fname, "\n".join(src) + "\n"))
     return out, stats
 
 
@@ -225,7 +247,7 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
 
 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
-                warps_per_sm: int = 8):
+                warps_per_sm: int = 8, prefetch: int = 1, merge: int = 8):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
     from .csparse import fingerprint
     from .tape import FN
@@ -233,10 +255,10 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     ext = external_values(pr)
     funcs: List[Tuple[str, str]] = []
     group_calls: List[List[str]] = []
-    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0)
+    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0)
     per_group = []
     for g in range(len(pr.groups)):
-        fs, st = emit_group(pr, g, ext, max_refs, max_loads)
+        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge)
         funcs += fs
         group_calls.append([n for n, _ in fs])
         per_group.append(st)
@@ -249,7 +271,12 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
             funcs += fs
             copy_calls[fid] = [n for n, _ in fs]
     # part files of roughly equal size (ptxas time is what we balance)
-    head = "// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n"
+    head = ("// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n"
+            '#define TC_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))\n'
+            "// IEEE division out of line: the ~20-instruction sequence would otherwise be a quarter of the\n"
+            "// instruction stream of a factorisation, and instruction fetch is what bounds a warp\n"
+            "static __device__ __noinline__ double tc_div(double a, double b) { return a / b; }\n"
+            "#define TC_DIV(a, b) tc_div((a), (b))\n")
     files: Dict[str, str] = {}
     cur, size = [head], 0
     for _, src in funcs:

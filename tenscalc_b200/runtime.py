@@ -41,6 +41,7 @@ ABI = [
     ("tc_set", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
     ("tc_set_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
     ("tc_solve", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p, _dp]),
+    ("tc_solve_async", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p]),
     ("tc_solve_device", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p]),
     ("tc_get_outputs", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     ("tc_get_outputs_device", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
@@ -237,6 +238,17 @@ class BatchedSolver:
                                   status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p),
                                   ctypes.byref(t)))
         return t.value
+
+    def solve_async(self, status: np.ndarray, it: np.ndarray, mu0: float = 1.0, maxIter: int = 200,
+                    saveIter: int = -1, addEye2Hessian: Sequence[float] = (1e-9, 1e-9)) -> None:
+        """enqueue the solve and the copies of status/iter into (pinned) host arrays; they are valid
+        after the next getOutputs / get_outputs_ptrs / synchronize on this handle"""
+        mu = ctypes.c_double(mu0)
+        mi = ctypes.c_int32(maxIter)
+        si = ctypes.c_int32(saveIter)
+        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        _check(self._lib.tc_solve_async(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
+                                        status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p)))
 
     def get_outputs_ptrs(self, ptrs: Sequence[int], device: bool) -> None:
         """getOutputs into caller-owned buffers, one double[batch][n_k] per output"""
