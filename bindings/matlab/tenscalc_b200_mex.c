@@ -5,7 +5,8 @@
  * host code keeps calling setP_* / setV_* / solve / getOutputs on a class object; the class
  * methods (bindings/matlab/tenscalc_b200_solver.m) forward to this single mex file.
  *
- *   h = tenscalc_b200_mex('create', uint8(image), batch, device)
+ *   h = tenscalc_b200_mex('create', uint8(image), batch, device [, moduleFile])
+ *       moduleFile: the per-problem compiled module (tc_attach_module); omitted = tape interpreter
  *       tenscalc_b200_mex('set', h, setIndex, values)            values: [n x batch] or [n x 1]
  *   [status,iter,time] = tenscalc_b200_mex('solve', h, mu0, int32(maxIter), int32(saveIter), addEye2Hessian)
  *   y = tenscalc_b200_mex('getOutputs', h)                       cell array, y{k} is [n_k x batch]
@@ -34,6 +35,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         tc_solver *s = NULL;
         check(tc_create(&s, mxGetData(prhs[1]), mxGetNumberOfElements(prhs[1]), (int64_t)mxGetScalar(prhs[2]),
                         nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 0));
+        if (nrhs > 4) {
+            char path[4096];
+            if (mxGetString(prhs[4], path, sizeof path)) mexErrMsgTxt("create: bad module file name");
+            check(tc_attach_module(s, path, NULL));
+        }
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
         *(uint64_t *)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)s;
     } else if (!strcmp(cmd, "set")) {

@@ -12,9 +12,13 @@ classdef tenscalc_b200_solver < handle
         h; names; batch;
     end
     methods
-        function obj=tenscalc_b200_solver(imageFile,batch,device)
+        function obj=tenscalc_b200_solver(imageFile,batch,device,moduleFile)
             fid=fopen(imageFile,'r'); img=fread(fid,inf,'*uint8'); fclose(fid);
-            obj.h=tenscalc_b200_mex('create',img,batch,device);
+            if nargin<4   % tape interpreter; pass the compiled module (tenscalc_b200/_gen/*.so) for native code
+                obj.h=tenscalc_b200_mex('create',img,batch,device);
+            else
+                obj.h=tenscalc_b200_mex('create',img,batch,device,moduleFile);
+            end
             obj.batch=batch;
             obj.names=jsondecode(fileread([imageFile,'.json'])); % {sets:{..},outputs:{..}}
         end

@@ -1,0 +1,90 @@
+"""The sm_100a CUDA emitter (host logic, no GPU): expression forms follow the reference emitter
+(lib/csparse/instructionsTableUTHash.c:950-1539), chunking keeps every value reachable, and the
+per-problem module builds, loads and exports the entry points tc_attach_module binds."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import generated
+from tenscalc_b200 import emit_cuda, itable as it
+
+
+def test_expression_forms():
+    e = emit_cuda.expression
+    assert e(it.I_sum, [1, -1, 1], ["a", "b", "c"], "r") == "const double r=+a-b+c;"
+    assert e(it.I_sumprod, [2, 2], ["a", "b", "c", "d"], "r") == "const double r=a*b+c*d;"
+    assert e(it.I_plus_minus_dot_div, [], ["a0", "d", "x", "y"], "r") == "const double r=TC_DIV((a0-(x*y)),d);"
+    assert e(it.I_minus_dot_div, [], ["d", "x", "y"], "r") == "const double r=TC_DIV(-(x*y),d);"
+    assert e(it.I_plus_minus_dot, [], ["a0", "x", "y", "z", "w"], "r") == "const double r=a0-(x*y+z*w);"
+    assert e(it.I_minus_dot, [], ["x", "y"], "r") == "const double r=-(x*y);"
+    assert e(it.I_max_abs, [], ["a", "b"], "r") == "double r=fabs(a); if (r<fabs(b)) r=fabs(b);"
+    assert e(it.I_min0, [], ["a"], "r") == "double r=0.0; if (r>a) r=a;"
+    assert "DBL_MAX" in e(it.I_clp, [], ["a", "b"], "r") and "if (b<0)" in e(it.I_clp, [], ["a", "b"], "r")
+    assert e(it.I_Dsqrt, [], ["x"], "r") == "const double r=.5*pow(x,-.5);"
+    assert e(it.I_sign, [], ["x"], "r") == "const double r=(x>=0)?1.0:-1.0;"
+
+
+def test_literals_are_exact():
+    for v in (0.1, -2.5e-7, 1e300, 3.0, -1.0, 1 / 3):
+        assert float.fromhex(emit_cuda._lit(v)) == v if "x" in emit_cuda._lit(v) else float(emit_cuda._lit(v)) == v
+
+
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor"])
+def test_chunks_cover_every_instruction_once(name):
+    gen, _ = generated(name)
+    pr = gen.problem
+    for g, members in enumerate(pr.groups):
+        chunks = emit_cuda.chunk_group(pr, members, 1536, 96)
+        assert [i for ch in chunks for i in ch] == list(members)
+        for ch in chunks[:-1]:
+            loads = {o for i in ch for o in pr.tab.operands[i]
+                     if pr.tab.types[o] not in (it.I_load, it.I_2)} - set(ch)
+            assert len(loads) <= 96 or len(ch) == 1      # one instruction wider than the budget stands alone
+
+
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor"])
+def test_every_value_read_is_defined(name):
+    """inside a chunk function every operand is a loaded local, an earlier result or an immediate;
+    every value read by another chunk / group / get / copy is stored"""
+    gen, _ = generated(name)
+    pr = gen.problem
+    ext = emit_cuda.external_values(pr)
+    stored_slots = set()
+    for g in range(len(pr.groups)):
+        fns, st = emit_cuda.emit_group(pr, g, ext)
+        assert st["loads"] + st["reg_reads"] >= 0
+        for _, src in fns:
+            for body in re.split(r"\n\{\n", src)[1:]:
+                defined = set(re.findall(r"double (v\d+)=", body))
+                used = set(re.findall(r"\bv\d+\b", body))
+                assert used <= defined, (g, sorted(used - defined)[:5])
+            stored_slots.update(int(x) // emit_cuda.TILE for x in re.findall(r"\bm\[(\d+)\]=", src))
+    for i in ext:
+        if pr.tab.types[i] not in (it.I_load, it.I_2, it.I_set) and i in pr.group_of:
+            assert int(pr.slot[i]) in stored_slots
+
+
+def test_module_builds_and_exports_entry_points():
+    from tenscalc_b200.build import build_module
+    from tenscalc_b200.csparse import fingerprint
+    gen, _ = generated("sls")
+    so = build_module(gen)
+    assert os.path.exists(so)
+    lib = ctypes.CDLL(so)
+    for sym in ("tcm_abi_version", "tcm_fingerprint", "tcm_image_bytes", "tcm_block", "tcm_load", "tcm_solve",
+                "tcm_eval"):
+        assert hasattr(lib, sym), sym
+    lib.tcm_fingerprint.restype = ctypes.c_char_p
+    assert lib.tcm_fingerprint().decode() == fingerprint(gen.problem)
+    assert lib.tcm_abi_version() == emit_cuda.TCM_ABI
+    assert lib.tcm_block() == 32
+
+
+def test_module_path_is_content_addressed():
+    from tenscalc_b200.build import module_path
+    gen, _ = generated("sls")
+    assert module_path(gen) == module_path(gen)
+    assert module_path(gen) != module_path(gen, max_loads=44)
