@@ -65,6 +65,15 @@ def _toolchain_tag(emit_opts: dict) -> str:
     return h.hexdigest()[:8]
 
 
+def default_module_opts(gen) -> dict:
+    """launch shape per problem size (measured on B200, profiles/): small scratchbooks (mpc_dcmotor,
+    sls) run fastest with many light warps -- 24 warps/SM at 80 registers, 28 operands per chunk --
+    large ones (mpc_quadcopter, l1l2) with 8 warps/SM at 255 registers and 96 operands per chunk"""
+    if gen.problem.n_slots <= 8192:
+        return dict(warps_per_sm=24, max_loads=28)
+    return {}
+
+
 def module_path(gen, **emit_opts) -> str:
     from .csparse import fingerprint
     return os.path.join(GEN_DIR, f"{gen.classname}_{fingerprint(gen.problem)[:10]}_{_toolchain_tag(emit_opts)}.so")
@@ -76,6 +85,7 @@ def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0,
     import time
     from concurrent.futures import ThreadPoolExecutor
     from .emit_cuda import emit_module
+    emit_opts = {**default_module_opts(gen), **emit_opts}
     so = module_path(gen, **emit_opts)
     if not force and os.path.exists(so):
         return so

@@ -10,6 +10,12 @@
 // its instance; branches are taken on warp votes only.  Per-instance decisions (exit tests,
 // regularisation control, line search, barrier update) use the same comparisons, constants
 // and order as the reference, so status codes and iteration counts match it.
+//
+// TC_TILES (compiled back end): every lane carries TC_TILES instances (one per scratchbook tile
+// of its warp), all per-instance state below is an array over t, and a dependency group is run
+// for all tiles of the warp by ONE pass over its code (the chunk functions loop over the tiles):
+// the instruction stream -- megabytes of straight-line SASS per Newton step, which is what
+// bounds a warp -- is fetched once per TC_TILES*32 instances.
 #pragma once
 #include "tc_vm.cuh"
 
@@ -26,20 +32,34 @@
 // line-search automaton, one state per `getMinF_s__` evaluation of ipmPD_CSsolver.c:690-756
 enum { LS_DONE = 0, LS_TRYMAX, LS_RECHECK, LS_TRYMIN, LS_SCAN, LS_SCAN_RECHECK };
 
-__device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &P, bool valid, double mu0,
-                                             int maxIter, double aeU0, double aeEq0, int &status_out,
-                                             int &iter_out) {
+typedef double tc_dT[TC_TILES];
+typedef bool tc_bT[TC_TILES];
+typedef int tc_iT[TC_TILES];
+#define TC_FORT _Pragma("unroll") for (int t = 0; t < TC_TILES; t++)
+
+__device__ __forceinline__ bool tc_any_tile(const tc_bT &x) {
+    bool a = false;
+    TC_FORT a = a || x[t];
+    return TC_ANY(a);
+}
+
+__device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &P, const tc_bT &valid, double mu0,
+                                             int maxIter, double aeU0, double aeEq0, tc_iT &status_out,
+                                             tc_iT &iter_out) {
     const tc_defines &D = P.def;
     const bool hasF = D.nF > 0, hasG = D.nG > 0;
     const bool adjust = D.setAddEye2Hessian && D.adjustAddEye2Hessian;
 
-    bool run = valid;
-    int status = 0, iter = 0;
-    double aeU = aeU0, aeEq = aeEq0;
-    bool updU = false, updEq = false;
-    double mu = mu0, muMin = 0, gapTol = D.desiredDualityGap, alphaMax_ = D.alphaMax;
-    double alphaPrimal = 0, alphaDualEq = 0, alphaDualIneq = 0;
-    double norminf_grad = 0, norminf_eq = 0, gap = 0, ineq = 0, ineq1 = 0, dual = 0;
+    tc_bT run, updU, updEq, pr, pr2;
+    tc_iT status, iter, ls;
+    tc_dT aeU, aeEq, mu, muMin, gapTol, alphaMax_, alphaPrimal, alphaDualEq, alphaDualIneq;
+    tc_dT norminf_grad, norminf_eq, gap, ineq, ineq1, dual, v0, v1, v2;
+    TC_FORT {
+        run[t] = valid[t]; updU[t] = updEq[t] = false; status[t] = 0; iter[t] = 0; ls[t] = LS_DONE;
+        aeU[t] = aeU0; aeEq[t] = aeEq0; mu[t] = mu0; muMin[t] = 0; gapTol[t] = D.desiredDualityGap;
+        alphaMax_[t] = D.alphaMax; alphaPrimal[t] = alphaDualEq[t] = alphaDualIneq[t] = 0;
+        norminf_grad[t] = norminf_eq[t] = gap[t] = ineq[t] = ineq1[t] = dual[t] = 0;
+    }
 
     if (D.setAddEye2Hessian) {                                              // :150-155
         tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, run);
@@ -49,86 +69,100 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     if (D.scaleCost) {                                                      // :206-214
         tc_copy(c, P, FN_scaleCost, run);
         tc_get(c, P, FN_getScale4Cost, run);
-        double s4c = tc_value(c, P, FN_getScale4Cost, 0, run);
-        if (hasF) gapTol *= s4c;
+        tc_value(c, P, FN_getScale4Cost, 0, run, v0);
+        if (hasF) TC_FORT gapTol[t] *= v0[t];
     }
     if (hasF) {                                                             // :216-230
         if (D.scaleInequalities) tc_copy(c, P, FN_scaleIneq, run);
         tc_set_scalar(c, P, FN_setMu, mu, run);
-        muMin = gapTol / D.nF / 2;
+        TC_FORT muMin[t] = gapTol[t] / D.nF / 2;
         tc_copy(c, P, FN_initDualIneq, run);
     }
     if (hasG) tc_copy(c, P, FN_initDualEqX, run);                           // :232-235
 
-    while (TC_ANY(run)) {                                      // :282
-        if (run) iter++;
-        if (run && iter > maxIter) { status = 8; run = false; }             // :308-313
+    while (tc_any_tile(run)) {                                              // :282
+        TC_FORT {
+            if (run[t]) iter[t]++;
+            if (run[t] && iter[t] > maxIter) { status[t] = 8; run[t] = false; }   // :308-313
+        }
 
         // ---- exit conditions (:323-381) ----
         tc_get(c, P, FN_getNorminf_Grad, run);
-        if (run) norminf_grad = tc_value(c, P, FN_getNorminf_Grad, 0, run);
-        if (run && isnan(norminf_grad)) { status = 4; run = false; }
+        tc_value(c, P, FN_getNorminf_Grad, 0, run, v0);
+        TC_FORT {
+            if (run[t]) norminf_grad[t] = v0[t];
+            if (run[t] && isnan(norminf_grad[t])) { status[t] = 4; run[t] = false; }
+        }
         if (hasG) {
             tc_get(c, P, FN_getNorminf_G, run);
-            if (run) norminf_eq = tc_value(c, P, FN_getNorminf_G, 0, run);
+            tc_value(c, P, FN_getNorminf_G, 0, run, v0);
+            TC_FORT if (run[t]) norminf_eq[t] = v0[t];
         }
         if (hasF) {
             tc_get(c, P, FN_getGapMinFMinLambda, run);
-            if (run) {
-                gap = tc_value(c, P, FN_getGapMinFMinLambda, 0, run);
-                ineq = tc_value(c, P, FN_getGapMinFMinLambda, 1, run);
-                dual = tc_value(c, P, FN_getGapMinFMinLambda, 2, run);
+            tc_value(c, P, FN_getGapMinFMinLambda, 0, run, v0);
+            tc_value(c, P, FN_getGapMinFMinLambda, 1, run, v1);
+            tc_value(c, P, FN_getGapMinFMinLambda, 2, run, v2);
+            TC_FORT {
+                if (run[t]) { gap[t] = v0[t]; ineq[t] = v1[t]; dual[t] = v2[t]; }
+                if (run[t] && ineq[t] <= 0) { status[t] = 1; run[t] = false; }
+                if (run[t] && dual[t] <= 0) { status[t] = 2; run[t] = false; }
             }
-            if (run && ineq <= 0) { status = 1; run = false; }
-            if (run && dual <= 0) { status = 2; run = false; }
         }
-        if (run && norminf_grad <= D.gradTolerance && (!hasF || gap <= gapTol) &&
-            (!hasG || norminf_eq <= D.equalTolerance) && (!adjust || aeU <= D.addEye2HessianUtolerance)) {
-            status = 0;
-            run = false;
+        TC_FORT if (run[t] && norminf_grad[t] <= D.gradTolerance && (!hasF || gap[t] <= gapTol[t]) &&
+                    (!hasG || norminf_eq[t] <= D.equalTolerance) &&
+                    (!adjust || aeU[t] <= D.addEye2HessianUtolerance)) {
+            status[t] = 0;
+            run[t] = false;
         }
 
         // ---- regularisation control (:393-548, useInertia==0) ----
         if (adjust) {
-            tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, run && updU);   // delayed from last iteration
-            tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, run && updEq);
-            if (run) updU = updEq = false;
+            TC_FORT { pr[t] = run[t] && updU[t]; pr2[t] = run[t] && updEq[t]; }
+            tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);            // delayed from last iteration
+            tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr2);
+            TC_FORT if (run[t]) updU[t] = updEq[t] = false;
             tc_get(c, P, FN_getCurvature, run);
-            double curvature = tc_value(c, P, FN_getCurvature, 0, run);
+            tc_value(c, P, FN_getCurvature, 0, run, v0);                    // curvature
             tc_get(c, P, FN_getDirectionError, run);
-            double derr = tc_value(c, P, FN_getDirectionError, 0, run);
-            bool nowU = false, nowEq = false;
-            if (run) {
-                if (curvature > 0) {                                        // :415-456
-                    if (aeU > TC_addEye2HessianMIN && derr < TC_maxDirectionError) {
-                        aeU = TC_MAX(.75 * aeU, TC_addEye2HessianMIN);
-                        updU = true;
-                    }
-                    if (aeEq > TC_addEye2HessianMIN && derr < TC_maxDirectionError) {
-                        aeEq = TC_MAX(.75 * aeEq, TC_addEye2HessianMIN);
-                        updEq = true;
-                    }
-                    if (aeU < TC_addEye2HessianUMAX && derr > TC_maxDirectionError) {
-                        aeU = TC_MIN(10 * aeU, TC_addEye2HessianUMAX);
-                        updU = true;
-                    }
-                    if (aeEq < TC_addEye2HessianEqMAX && derr > TC_maxDirectionError) {
-                        aeEq = TC_MIN(10 * aeEq, TC_addEye2HessianEqMAX);
-                        updEq = true;
-                    }
-                } else if (curvature < 0) {                                 // :462-480, single pass
-                    if (aeU < TC_addEye2HessianUMAX) {
-                        aeU = TC_MIN(10 * TC_MAX(aeU, TC_addEye2HessianMIN), TC_addEye2HessianUMAX);
-                        nowU = true;
-                    }
-                    if (aeEq < TC_addEye2HessianEqMAX) {
-                        aeEq = TC_MIN(10 * TC_MAX(aeEq, TC_addEye2HessianMIN), TC_addEye2HessianEqMAX);
-                        nowEq = true;
+            tc_value(c, P, FN_getDirectionError, 0, run, v1);               // direction error
+            TC_FORT {
+                const double curvature = v0[t], derr = v1[t];
+                bool nowU = false, nowEq = false;
+                if (run[t]) {
+                    if (curvature > 0) {                                    // :415-456
+                        if (aeU[t] > TC_addEye2HessianMIN && derr < TC_maxDirectionError) {
+                            aeU[t] = TC_MAX(.75 * aeU[t], TC_addEye2HessianMIN);
+                            updU[t] = true;
+                        }
+                        if (aeEq[t] > TC_addEye2HessianMIN && derr < TC_maxDirectionError) {
+                            aeEq[t] = TC_MAX(.75 * aeEq[t], TC_addEye2HessianMIN);
+                            updEq[t] = true;
+                        }
+                        if (aeU[t] < TC_addEye2HessianUMAX && derr > TC_maxDirectionError) {
+                            aeU[t] = TC_MIN(10 * aeU[t], TC_addEye2HessianUMAX);
+                            updU[t] = true;
+                        }
+                        if (aeEq[t] < TC_addEye2HessianEqMAX && derr > TC_maxDirectionError) {
+                            aeEq[t] = TC_MIN(10 * aeEq[t], TC_addEye2HessianEqMAX);
+                            updEq[t] = true;
+                        }
+                    } else if (curvature < 0) {                             // :462-480, single pass
+                        if (aeU[t] < TC_addEye2HessianUMAX) {
+                            aeU[t] = TC_MIN(10 * TC_MAX(aeU[t], TC_addEye2HessianMIN), TC_addEye2HessianUMAX);
+                            nowU = true;
+                        }
+                        if (aeEq[t] < TC_addEye2HessianEqMAX) {
+                            aeEq[t] = TC_MIN(10 * TC_MAX(aeEq[t], TC_addEye2HessianMIN), TC_addEye2HessianEqMAX);
+                            nowEq = true;
+                        }
                     }
                 }
+                pr[t] = nowU;
+                pr2[t] = nowEq;
             }
-            tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, nowU);          // immediate
-            tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, nowEq);
+            tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);            // immediate
+            tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr2);
             // The reference re-reads curvature and direction error here (:524-531) only to
             // print them; the groups they would refresh are refreshed lazily by the next get.
         }
@@ -142,77 +176,87 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
 
         // ---- combined search direction (:679-772) ----
         tc_get(c, P, FN_getMaxAlphas_s, run);
-        int ls = LS_DONE;
-        if (run) {
-            alphaPrimal = tc_value(c, P, FN_getMaxAlphas_s, 0, run);
-            alphaDualIneq = tc_value(c, P, FN_getMaxAlphas_s, 1, run);
-            if (D.coupledAlphas && alphaDualIneq < alphaPrimal) alphaPrimal = alphaDualIneq;
-            alphaPrimal *= TC_stepback;
-            alphaMax_ = (alphaPrimal < D.alphaMax) ? alphaPrimal : D.alphaMax;
-            if (alphaMax_ >= D.alphaMin) {
-                alphaPrimal = alphaMax_ / TC_stepback;
-                ls = LS_TRYMAX;
+        tc_value(c, P, FN_getMaxAlphas_s, 0, run, v0);
+        tc_value(c, P, FN_getMaxAlphas_s, 1, run, v1);
+        tc_bT zero_now, ev;
+        TC_FORT {
+            ls[t] = LS_DONE;
+            if (run[t]) {
+                alphaPrimal[t] = v0[t];
+                alphaDualIneq[t] = v1[t];
+                if (D.coupledAlphas && alphaDualIneq[t] < alphaPrimal[t]) alphaPrimal[t] = alphaDualIneq[t];
+                alphaPrimal[t] *= TC_stepback;
+                alphaMax_[t] = (alphaPrimal[t] < D.alphaMax) ? alphaPrimal[t] : D.alphaMax;
+                if (alphaMax_[t] >= D.alphaMin) {
+                    alphaPrimal[t] = alphaMax_[t] / TC_stepback;
+                    ls[t] = LS_TRYMAX;
+                }
             }
+            zero_now[t] = run[t] && ls[t] == LS_DONE;                       // :752-756
         }
-        bool zero_now = run && ls == LS_DONE;                               // :752-756
         while (true) {
-            if (zero_now) alphaPrimal = 0;
-            tc_set_scalar(c, P, FN_setAlphaPrimal, alphaPrimal, zero_now || ls != LS_DONE);
-            zero_now = false;
-            const bool ev = ls != LS_DONE;
-            if (!TC_ANY(ev)) break;
+            TC_FORT {
+                if (zero_now[t]) alphaPrimal[t] = 0;
+                pr[t] = zero_now[t] || ls[t] != LS_DONE;
+            }
+            tc_set_scalar(c, P, FN_setAlphaPrimal, alphaPrimal, pr);
+            TC_FORT { zero_now[t] = false; ev[t] = ls[t] != LS_DONE; }
+            if (!tc_any_tile(ev)) break;
             tc_get(c, P, FN_getMinF_s, ev);
-            const double f = tc_value(c, P, FN_getMinF_s, 0, ev);
-            if (ev) switch (ls) {
-            case LS_TRYMAX:                                                 // :693-714
-                ineq = f;
-                if (isnan(ineq)) { status = 4; run = false; ls = LS_DONE; }
-                else if (ineq > 0) { alphaPrimal *= TC_stepback; ls = LS_RECHECK; }
-                else { alphaPrimal = D.alphaMin / TC_stepback; ls = LS_TRYMIN; }
-                break;
-            case LS_RECHECK:
-                ineq1 = f;
-                if (ineq1 <= ineq / 10) { alphaPrimal = D.alphaMin / TC_stepback; ls = LS_TRYMIN; }
-                else ls = LS_DONE;
-                break;
-            case LS_TRYMIN:                                                 // :716-749
-                ineq = f;
-                if (ineq > 0) {
-                    alphaPrimal = alphaMax_ * .95;
-                    if (alphaPrimal >= D.alphaMin) ls = LS_SCAN;
-                    else { zero_now = true; ls = LS_DONE; }
-                } else { zero_now = true; ls = LS_DONE; }
-                break;
-            case LS_SCAN:                                                   // :722-738
-                ineq = f;
-                if (ineq > 0) { alphaPrimal *= TC_stepback; ls = LS_SCAN_RECHECK; }
-                else {
-                    alphaPrimal /= 2;
-                    if (!(alphaPrimal >= D.alphaMin)) { zero_now = true; ls = LS_DONE; }
+            tc_value(c, P, FN_getMinF_s, 0, ev, v0);
+            TC_FORT {
+                const double f = v0[t];
+                if (ev[t]) switch (ls[t]) {
+                case LS_TRYMAX:                                             // :693-714
+                    ineq[t] = f;
+                    if (isnan(ineq[t])) { status[t] = 4; run[t] = false; ls[t] = LS_DONE; }
+                    else if (ineq[t] > 0) { alphaPrimal[t] *= TC_stepback; ls[t] = LS_RECHECK; }
+                    else { alphaPrimal[t] = D.alphaMin / TC_stepback; ls[t] = LS_TRYMIN; }
+                    break;
+                case LS_RECHECK:
+                    ineq1[t] = f;
+                    if (ineq1[t] <= ineq[t] / 10) { alphaPrimal[t] = D.alphaMin / TC_stepback; ls[t] = LS_TRYMIN; }
+                    else ls[t] = LS_DONE;
+                    break;
+                case LS_TRYMIN:                                             // :716-749
+                    ineq[t] = f;
+                    if (ineq[t] > 0) {
+                        alphaPrimal[t] = alphaMax_[t] * .95;
+                        if (alphaPrimal[t] >= D.alphaMin) ls[t] = LS_SCAN;
+                        else { zero_now[t] = true; ls[t] = LS_DONE; }
+                    } else { zero_now[t] = true; ls[t] = LS_DONE; }
+                    break;
+                case LS_SCAN:                                               // :722-738
+                    ineq[t] = f;
+                    if (ineq[t] > 0) { alphaPrimal[t] *= TC_stepback; ls[t] = LS_SCAN_RECHECK; }
+                    else {
+                        alphaPrimal[t] /= 2;
+                        if (!(alphaPrimal[t] >= D.alphaMin)) { zero_now[t] = true; ls[t] = LS_DONE; }
+                    }
+                    break;
+                case LS_SCAN_RECHECK:
+                    ineq1[t] = f;
+                    if (ineq1[t] > ineq[t] / 10) {
+                        ls[t] = LS_DONE;
+                        if (alphaPrimal[t] < D.alphaMin) zero_now[t] = true;    // :739-743
+                    } else {
+                        alphaPrimal[t] /= 2;
+                        if (alphaPrimal[t] >= D.alphaMin) ls[t] = LS_SCAN;
+                        else { zero_now[t] = true; ls[t] = LS_DONE; }
+                    }
+                    break;
                 }
-                break;
-            case LS_SCAN_RECHECK:
-                ineq1 = f;
-                if (ineq1 > ineq / 10) {
-                    ls = LS_DONE;
-                    if (alphaPrimal < D.alphaMin) zero_now = true;          // :739-743
-                } else {
-                    alphaPrimal /= 2;
-                    if (alphaPrimal >= D.alphaMin) ls = LS_SCAN;
-                    else { zero_now = true; ls = LS_DONE; }
-                }
-                break;
             }
         }
 
-        if (run) {                                                          // :758-767
+        TC_FORT if (run[t]) {                                               // :758-767
             if (D.coupledAlphas) {
-                alphaDualEq = alphaPrimal;
-                alphaDualIneq = alphaPrimal;
+                alphaDualEq[t] = alphaPrimal[t];
+                alphaDualIneq[t] = alphaPrimal[t];
             } else {
-                alphaDualIneq *= TC_stepback;
-                if (alphaDualIneq > alphaMax_) alphaDualIneq = alphaMax_;
-                alphaDualEq = alphaDualIneq;
+                alphaDualIneq[t] *= TC_stepback;
+                if (alphaDualIneq[t] > alphaMax_[t]) alphaDualIneq[t] = alphaMax_[t];
+                alphaDualEq[t] = alphaDualIneq[t];
             }
         }
         if (hasG) tc_set_scalar(c, P, FN_setAlphaDualEq, alphaDualEq, run);
@@ -220,63 +264,73 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         tc_copy(c, P, FN_updatePrimalDual, run);                            // :772
 
         // ---- barrier parameter update, skipAffine!=0 (:782-859) ----
-        bool set_mu = false, reinit_dual = false;
-        if (run) {
-            const bool th_grad = norminf_grad < TC_MAX(1e-6, 1e0 * D.gradTolerance);
-            const bool th_eq = !hasG || norminf_eq < TC_MAX(1e-5, 1e0 * D.equalTolerance);
-            if (alphaPrimal > alphaMax_ / 2 && th_grad && th_eq) {
-                const double r = sqrt(mu);   // pow(mu,.5) in the reference; sqrt is its correctly rounded value
-                mu *= TC_MIN(D.muFactorAggressive, r);
-                if (mu < muMin) mu = muMin;
-                set_mu = true;
-            } else if (alphaPrimal < .1) {
-                mu *= 1.1;
-                if (mu > mu0) mu = mu0;
-                set_mu = true;
-                reinit_dual = true;
-            } else if (alphaPrimal > .99 && th_eq) {
-                mu *= D.muFactorConservative;
-                if (mu < muMin) mu = muMin;
-                set_mu = true;
+        TC_FORT {
+            bool set_mu = false, reinit_dual = false;
+            if (run[t]) {
+                const bool th_grad = norminf_grad[t] < TC_MAX(1e-6, 1e0 * D.gradTolerance);
+                const bool th_eq = !hasG || norminf_eq[t] < TC_MAX(1e-5, 1e0 * D.equalTolerance);
+                if (alphaPrimal[t] > alphaMax_[t] / 2 && th_grad && th_eq) {
+                    const double r = sqrt(mu[t]);   // pow(mu,.5) in the reference; sqrt is its correctly rounded value
+                    mu[t] *= TC_MIN(D.muFactorAggressive, r);
+                    if (mu[t] < muMin[t]) mu[t] = muMin[t];
+                    set_mu = true;
+                } else if (alphaPrimal[t] < .1) {
+                    mu[t] *= 1.1;
+                    if (mu[t] > mu0) mu[t] = mu0;
+                    set_mu = true;
+                    reinit_dual = true;
+                } else if (alphaPrimal[t] > .99 && th_eq) {
+                    mu[t] *= D.muFactorConservative;
+                    if (mu[t] < muMin[t]) mu[t] = muMin[t];
+                    set_mu = true;
+                }
+            }
+            pr[t] = set_mu;
+            pr2[t] = reinit_dual;
+        }
+        tc_set_scalar(c, P, FN_setMu, mu, pr);
+        tc_copy(c, P, FN_initDualIneq, pr2);                                // :816
+        TC_FORT {
+            pr[t] = run[t] && alphaPrimal[t] < D.alphaMin && alphaDualIneq[t] < D.alphaMin &&
+                    alphaDualEq[t] < D.alphaMin;
+            if (pr[t]) {                                                    // :853-859
+                mu[t] /= (D.muFactorConservative * D.muFactorConservative);
+                if (mu[t] < muMin[t]) mu[t] = muMin[t];
             }
         }
-        tc_set_scalar(c, P, FN_setMu, mu, set_mu);
-        tc_copy(c, P, FN_initDualIneq, reinit_dual);                        // :816
-        bool stall = run && alphaPrimal < D.alphaMin && alphaDualIneq < D.alphaMin && alphaDualEq < D.alphaMin;
-        if (stall) {                                                        // :853-859
-            mu /= (D.muFactorConservative * D.muFactorConservative);
-            if (mu < muMin) mu = muMin;
-        }
-        tc_set_scalar(c, P, FN_setMu, mu, stall);
+        tc_set_scalar(c, P, FN_setMu, mu, pr);
     }
 
     // ---- diagnostic bits when maxIter was reached (:885-920) ----
-    const bool diag = valid && status == 8;
-    if (TC_ANY(diag)) {
+    tc_bT diag;
+    TC_FORT diag[t] = valid[t] && status[t] == 8;
+    if (tc_any_tile(diag)) {
         tc_get(c, P, FN_getNorminf_Grad, diag);
-        norminf_grad = tc_value(c, P, FN_getNorminf_Grad, 0, diag);
-        if (diag && norminf_grad > D.gradTolerance) status |= 16;
+        tc_value(c, P, FN_getNorminf_Grad, 0, diag, v0);
+        TC_FORT if (diag[t] && v0[t] > D.gradTolerance) status[t] |= 16;
         if (hasG) {
             tc_get(c, P, FN_getNorminf_G, diag);
-            norminf_eq = tc_value(c, P, FN_getNorminf_G, 0, diag);
-            if (diag && norminf_eq > D.equalTolerance) status |= 32;
+            tc_value(c, P, FN_getNorminf_G, 0, diag, v0);
+            TC_FORT if (diag[t] && v0[t] > D.equalTolerance) status[t] |= 32;
         }
         if (hasF) {
             tc_get(c, P, FN_getGapMinFMinLambda, diag);
-            gap = tc_value(c, P, FN_getGapMinFMinLambda, 0, diag);
-            if (diag) {
-                if (gap > gapTol) status |= 64;
-                if (mu > muMin) status |= 128;
-                if (alphaPrimal <= D.alphaMin && alphaDualIneq < D.alphaMin && alphaDualEq < D.alphaMin)
-                    status |= 1792;
-                else if (alphaPrimal <= .1 && alphaDualIneq < .1 && alphaDualEq < .1)
-                    status |= 1536;
-                else if (alphaPrimal <= .5 && alphaDualIneq < .5 && alphaDualEq < .5)
-                    status |= 1024;
+            tc_value(c, P, FN_getGapMinFMinLambda, 0, diag, v0);
+            TC_FORT if (diag[t]) {
+                if (v0[t] > gapTol[t]) status[t] |= 64;
+                if (mu[t] > muMin[t]) status[t] |= 128;
+                if (alphaPrimal[t] <= D.alphaMin && alphaDualIneq[t] < D.alphaMin && alphaDualEq[t] < D.alphaMin)
+                    status[t] |= 1792;
+                else if (alphaPrimal[t] <= .1 && alphaDualIneq[t] < .1 && alphaDualEq[t] < .1)
+                    status[t] |= 1536;
+                else if (alphaPrimal[t] <= .5 && alphaDualIneq[t] < .5 && alphaDualEq[t] < .5)
+                    status[t] |= 1024;
             }
         }
-        if (adjust && diag && aeU > D.addEye2HessianUtolerance) status |= 2048;
+        TC_FORT if (adjust && diag[t] && aeU[t] > D.addEye2HessianUtolerance) status[t] |= 2048;
     }
-    status_out = status;
-    iter_out = iter;
+    TC_FORT {
+        status_out[t] = status[t];
+        iter_out[t] = iter[t];
+    }
 }

@@ -18,7 +18,14 @@
 #define TC_KMINBLOCKS 4
 #endif
 
-__device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &P, int64_t inst) {
+// warp w of the grid owns the TC_TILES adjacent tiles w*TC_TILES ..; lane l carries instance
+// (w*TC_TILES + t)*32 + l of every tile t
+__device__ __forceinline__ int64_t tc_inst(int t) {
+    const int64_t warp = ((int64_t)blockIdx.x * TC_KBLOCK + threadIdx.x) >> 5;
+    return (warp * TC_TILES + t) * 32 + (threadIdx.x & 31);
+}
+
+__device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &P) {
     // result ring [slot][thread] (conflict-free), then the constant pool (broadcast reads)
 #ifdef TC_COMPILED_GROUPS
     c.sm = nullptr;
@@ -28,17 +35,25 @@ __device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &
     __syncthreads();
     c.sm = sm;
 #endif
-    c.mb = &TC_M(P, 0, inst);
     c.consts = P.consts;
     c.tape = P.tape;
     c.lane = threadIdx.x & 31u;
-    c.st[0] = P.group_status[inst];
-    c.st[1] = P.group_status[P.stride + inst];
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) {
+        const int64_t inst = tc_inst(t);
+        c.mb[t] = &TC_M(P, 0, inst);
+        c.st[t][0] = P.group_status[inst];
+        c.st[t][1] = P.group_status[P.stride + inst];
+    }
 }
 
-__device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device_image &P, int64_t inst) {
-    P.group_status[inst] = c.st[0];
-    P.group_status[P.stride + inst] = c.st[1];
+__device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device_image &P) {
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) {
+        const int64_t inst = tc_inst(t);
+        P.group_status[inst] = c.st[t][0];
+        P.group_status[P.stride + inst] = c.st[t][1];
+    }
 }
 
 // whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
@@ -46,25 +61,29 @@ __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_solve_kernel(tc_d
                                                             double aeU, double aeEq,
                                                             int32_t *__restrict__ status,
                                                             int32_t *__restrict__ iter) {
-    const int64_t inst = (int64_t)blockIdx.x * TC_KBLOCK + threadIdx.x;
-    const bool valid = inst < P.batch;
     tc_lane c;
-    tc_lane_init(c, P, inst);
-    int st, it;
+    tc_lane_init(c, P);
+    bool valid[TC_TILES];
+    int st[TC_TILES], it[TC_TILES];
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) valid[t] = tc_inst(t) < P.batch;
     tc_ipm_solve(c, P, valid, mu0, maxIter, aeU, aeEq, st, it);
-    tc_lane_finish(c, P, inst);
-    if (valid) {
-        status[inst] = st;
-        iter[inst] = it;
-    }
+    tc_lane_finish(c, P);
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++)
+        if (valid[t]) {
+            status[tc_inst(t)] = st[t];
+            iter[tc_inst(t)] = it[t];
+        }
 }
 
 // lazy evaluation of the parents of one get function (classname_getOutputs)
 __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_eval_kernel(tc_device_image P, int fn) {
-    const int64_t inst = (int64_t)blockIdx.x * TC_KBLOCK + threadIdx.x;
     tc_lane c;
-    tc_lane_init(c, P, inst);
-    tc_get(c, P, fn, inst < P.batch);
-    tc_lane_finish(c, P, inst);
+    tc_lane_init(c, P);
+    bool valid[TC_TILES];
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) valid[t] = tc_inst(t) < P.batch;
+    tc_get(c, P, fn, valid);
+    tc_lane_finish(c, P);
 }
-

@@ -38,13 +38,17 @@
 #define TC_ANY(x) (__any_sync(TC_FULL, (x)) != 0)
 #endif
 
+#ifndef TC_TILES
+#define TC_TILES 1         // instances per lane = scratchbook tiles per warp (compiled back end: emit_cuda.py)
+#endif
+
 struct tc_lane {
-    double *mb;            // &m[tile][0][lane]; slot k of this instance is mb[k*32]
+    double *mb[TC_TILES];  // &m[tile][0][lane]; slot k of the instance in tile t is mb[t][k*32]
     const double *consts;
     const uint4 *tape;
     double *sm;            // shared memory of the CTA: result ring [TC_RING][TC_BLOCK], then constants
     unsigned lane;
-    uint64_t st[2];        // groupStatus[] of this instance, one bit per group
+    uint64_t st[TC_TILES][2];   // groupStatus[] of every instance, one bit per group
 };
 
 #ifdef TC_COMPILED_GROUPS
@@ -52,11 +56,15 @@ struct tc_lane {
 // generated per problem by tenscalc_b200/emit_cuda.py and linked into the same module.
 // run dependency group g on the instances with pred set; called by every thread that took the
 // vote (warp, or CTA under TC_LOCKSTEP: then every chunk ends in a CTA barrier)
-extern __device__ void tcm_group(int g, double *m, bool pred);
-extern __device__ bool tcm_copy(int fn, double *m);          // copy function fn; false: no compiled body
+// `mask` bit t: run it on the instance of tile t (tiles of a warp are adjacent: m + t*S*32)
+extern __device__ void tcm_group(int g, double *m, unsigned mask);
+extern __device__ bool tcm_copy(int fn, double *m, unsigned mask);   // copy function fn; false: no compiled body
 
-__device__ __forceinline__ void tc_exec_group(tc_lane &c, const uint32_t *, int g, bool pred) {
-    tcm_group(g, c.mb, pred);
+__device__ __forceinline__ void tc_exec_group(tc_lane &c, const uint32_t *, int g, const bool (&pred)[TC_TILES]) {
+    unsigned mask = 0;
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) mask |= pred[t] ? (1u << t) : 0u;
+    tcm_group(g, c.mb[0], mask);
     __syncwarp();
 }
 #else
@@ -208,11 +216,11 @@ __device__ __forceinline__ void tc_exec(const tc_bundle &B, char *mb, double *sm
 }
 
 // Execute dependency group g for the lanes with pred set.  Must be called by all 32 lanes.
-__device__ __noinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_start, int g, bool pred) {
+__device__ __noinline__ void tc_exec_group1(tc_lane &c, const uint32_t *group_start, int g, bool pred) {
     const uint32_t first = __ldg(group_start + g);
     const uint4 *cells = c.tape + first;
     const int nb = (int)((__ldg(group_start + g + 1) - first) / TC_BUNDLE);
-    char *const mb = (char *)c.mb;
+    char *const mb = (char *)c.mb[0];
     double *const sm = c.sm;
     const unsigned tid = threadIdx.x;
     double acc = 0.0, p = 0.0;
@@ -229,66 +237,89 @@ __device__ __noinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_sta
     }
 }
 
+static_assert(TC_TILES == 1, "the tape interpreter runs one instance per lane");
+__device__ __forceinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_start, int g, const bool (&pred)[1]) {
+    tc_exec_group1(c, group_start, g, pred[0]);
+}
+
 #endif  // TC_COMPILED_GROUPS
 
 // ---- lazy group evaluation and set/get/copy wrappers (writeCfunctionpergroup.m:513-852) ------
 // io[] word of a get/copy source: scratchbook slot, or constant-pool index when TC_CONST_BIT is set
-__device__ __forceinline__ double tc_ldop(const tc_lane &c, uint32_t w, bool pred) {
+__device__ __forceinline__ double tc_ldop(const tc_lane &c, int t, uint32_t w, bool pred) {
     const uint32_t idx = w & TC_SLOT_MASK;
     if (w & TC_CONST_BIT) return __ldg(c.consts + idx);                 // warp-uniform branch
-    return pred ? c.mb[(size_t)idx * TC_TILE] : 0.0;
+    return pred ? c.mb[t][(size_t)idx * TC_TILE] : 0.0;
 }
 
-__device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image &P, const tc_func *f, bool pred) {
+__device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image &P, const tc_func *f,
+                                               const bool (&pred)[TC_TILES]) {
 #pragma unroll
     for (int w = 0; w < 2; w++) {
         uint64_t bits = f->parents[w];          // warp-uniform
         while (bits) {
             int b = __ffsll((long long)bits) - 1;
             bits &= bits - 1;
-            bool need = pred && !((c.st[w] >> b) & 1ull);
-            const unsigned vote = __ballot_sync(TC_FULL, need);
-            if (TC_ANY(need)) {
+            bool need[TC_TILES], any = false;
+            unsigned n = 0;
+#pragma unroll
+            for (int t = 0; t < TC_TILES; t++) {
+                need[t] = pred[t] && !((c.st[t][w] >> b) & 1ull);
+                any = any || need[t];
+                n += __popc(__ballot_sync(TC_FULL, need[t]));
+            }
+            if (TC_ANY(any)) {
                 tc_exec_group(c, P.group_start, 64 * w + b, need);
                 // static per-group flop/byte tables x these counts = algorithmic work (the
                 // reference's profiling counters, writeCfunctionpergroup.m:149-177,481-492)
-                if (c.lane == 0 && vote) atomicAdd(P.group_count + 64 * w + b, (unsigned long long)__popc(vote));
+                if (c.lane == 0 && n) atomicAdd(P.group_count + 64 * w + b, (unsigned long long)n);
             }
-            if (need) c.st[w] |= 1ull << b;
+#pragma unroll
+            for (int t = 0; t < TC_TILES; t++)
+                if (need[t]) c.st[t][w] |= 1ull << b;
         }
     }
 }
 
-__device__ __forceinline__ void tc_invalidate(tc_lane &c, const tc_func *f, bool pred) {
-    if (pred) {
-        c.st[0] &= ~f->children[0];
-        c.st[1] &= ~f->children[1];
-    }
+__device__ __forceinline__ void tc_invalidate(tc_lane &c, const tc_func *f, const bool (&pred)[TC_TILES]) {
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++)
+        if (pred[t]) {
+            c.st[t][0] &= ~f->children[0];
+            c.st[t][1] &= ~f->children[1];
+        }
 }
 
-__device__ __forceinline__ void tc_set_scalar(tc_lane &c, const tc_device_image &P, int fn, double value, bool pred) {
+__device__ __forceinline__ void tc_set_scalar(tc_lane &c, const tc_device_image &P, int fn,
+                                              const double (&value)[TC_TILES], const bool (&pred)[TC_TILES]) {
     const tc_func *f = P.funcs + fn;
     uint32_t slot = __ldg(P.io + f->io_off);
-    if (pred) c.mb[(size_t)slot * TC_TILE] = value;
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++)
+        if (pred[t]) c.mb[t][(size_t)slot * TC_TILE] = value[t];
     tc_invalidate(c, f, pred);
 }
 
-__device__ __forceinline__ void tc_get(tc_lane &c, const tc_device_image &P, int fn, bool pred) {
+__device__ __forceinline__ void tc_get(tc_lane &c, const tc_device_image &P, int fn, const bool (&pred)[TC_TILES]) {
     tc_run_parents(c, P, P.funcs + fn, pred);
 }
 
-__device__ __forceinline__ double tc_value(const tc_lane &c, const tc_device_image &P, int fn, int k, bool pred) {
+__device__ __forceinline__ void tc_value(const tc_lane &c, const tc_device_image &P, int fn, int k,
+                                         const bool (&pred)[TC_TILES], double (&out)[TC_TILES]) {
     uint32_t w = __ldg(P.io + P.funcs[fn].io_off + k);
-    return (w == TC_NO_SLOT) ? 0.0 : tc_ldop(c, w, pred);
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) out[t] = (w == TC_NO_SLOT) ? 0.0 : tc_ldop(c, t, w, pred[t]);
 }
 
-__device__ __noinline__ void tc_copy(tc_lane &c, const tc_device_image &P, int fn, bool pred) {
+__device__ __noinline__ void tc_copy(tc_lane &c, const tc_device_image &P, int fn, const bool (&pred)[TC_TILES]) {
     const tc_func *f = P.funcs + fn;
     tc_run_parents(c, P, f, pred);
 #ifdef TC_COMPILED_GROUPS
     {
-        bool done = true;
-        if (pred) done = tcm_copy(fn, c.mb);
+        unsigned mask = 0;
+#pragma unroll
+        for (int t = 0; t < TC_TILES; t++) mask |= pred[t] ? (1u << t) : 0u;
+        bool done = tcm_copy(fn, c.mb[0], mask);
         __syncwarp();
         if (__all_sync(TC_FULL, done)) {
             tc_invalidate(c, f, pred);
@@ -300,8 +331,11 @@ __device__ __noinline__ void tc_copy(tc_lane &c, const tc_device_image &P, int f
     const uint32_t cnt = f->io_cnt;
     for (uint32_t k = 0; k < cnt; k += 2) {
         uint32_t d = __ldg(io + k), s = __ldg(io + k + 1);
-        double v = tc_ldop(c, s, pred);
-        if (pred) c.mb[(size_t)d * TC_TILE] = v;
+#pragma unroll
+        for (int t = 0; t < TC_TILES; t++) {
+            double v = tc_ldop(c, t, s, pred[t]);
+            if (pred[t]) c.mb[t][(size_t)d * TC_TILE] = v;
+        }
     }
     tc_invalidate(c, f, pred);
 }

@@ -185,7 +185,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             lines.append(expression(t, p, o, f"v{i}"))
             have.add(i)
             if i in ext or i in cross:
-                lines.append(f"m[{int(slot[i]) * TILE}]=v{i};")
+                lines.append(f"mt[{int(slot[i]) * TILE}]=v{i};")
                 stores.add(int(slot[i]))
                 stats["stores"] += 1
             else:
@@ -196,11 +196,14 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
     # callee-saved register spill/restore is paid once per function instead of once per chunk
     for f0 in range(0, len(bodies), merge):
         fname = bodies[f0][0]
-        src = [f"__device__ __noinline__ void {fname}(double *__restrict__ m) {{"]
+        src = [f"__device__ __noinline__ void {fname}(double *__restrict__ m, unsigned mask) {{"]
         for k in range(f0, min(f0 + merge, len(bodies))):
             name, loads, stores, lines = bodies[k]
-            src.append("{")
-            src += [f"const double v{q}=m[{int(slot[q]) * TILE}];" for q in loads]
+            # one pass over the chunk's code per tile of the warp: the second pass runs out of the
+            # instruction cache (TC_TILE_LOOP / TC_MT are defined in the module header)
+            src.append("TC_TILE_LOOP {")
+            src.append("double *__restrict__ mt = TC_MT;")
+            src += [f"const double v{q}=mt[{int(slot[q]) * TILE}];" for q in loads]
             if prefetch and k + 1 < len(bodies):
                 # while this chunk's operands are in flight, pull the NEXT chunk's operands into L2: its
                 # load phase then costs an L2 hit instead of an HBM round trip (no registers involved)
@@ -208,7 +211,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                 nxt = [int(slot[q]) for q in bodies[k + 1][1] if int(slot[q]) not in mine]
                 if nxt:            # the clobber keeps this chunk's own loads ahead of the prefetches
                     src.append('asm volatile("" ::: "memory");')
-                src += [f"TC_PREFETCH(m+{sl * TILE});" for sl in nxt]
+                src += [f"TC_PREFETCH(mt+{sl * TILE});" for sl in nxt]
                 stats["prefetches"] += len(nxt)
             src += lines
             src.append("}")
@@ -231,7 +234,8 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
     pairs = [(d, s) for d, s in zip(c.dest, c.src) if d != s]
     out = []
     for k in range(0, max(len(pairs), 1), max_pairs):
-        lines = [f"__device__ __noinline__ void tcc{fn_id}_{k // max_pairs}(double *__restrict__ m) {{"]
+        lines = [f"__device__ __noinline__ void tcc{fn_id}_{k // max_pairs}(double *__restrict__ m, unsigned mask) {{",
+                 "TC_TILE_LOOP {", "double *__restrict__ mt = TC_MT;"]
         for d, s in pairs[k:k + max_pairs]:
             ts = tab.types[s]
             if ts == it.I_load:
@@ -239,15 +243,15 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
             elif ts == it.I_2:
                 src = "2.0"
             else:
-                src = f"m[{int(slot[s]) * TILE}]"
-            lines.append(f"m[{int(slot[d]) * TILE}]={src};")
-        lines.append("}")
+                src = f"mt[{int(slot[s]) * TILE}]"
+            lines.append(f"mt[{int(slot[d]) * TILE}]={src};")
+        lines += ["}", "}"]
         out.append((f"tcc{fn_id}_{k // max_pairs}", "\n".join(lines) + "\n"))
     return out
 
 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
-                warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0):
+                warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
     from .csparse import fingerprint
     from .tape import FN
@@ -271,7 +275,14 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
             funcs += fs
             copy_calls[fid] = [n for n, _ in fs]
     # part files of roughly equal size (ptxas time is what we balance)
+    if tiles not in (1, 2, 4, 8):
+        raise ValueError("tiles must be 1, 2, 4 or 8 instances per lane")
     head = ("// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n"
+            f"#define TC_TILES {tiles}\n#define TC_TILE_STRIDE {int(pr.n_slots) * TILE}ull\n"
+            "#if TC_TILES > 1\n"
+            '#define TC_TILE_LOOP _Pragma("unroll 1") for (int t = 0; t < TC_TILES; t++) if ((mask >> t) & 1u)\n'
+            "#define TC_MT (m + (size_t)t * TC_TILE_STRIDE)\n"
+            "#else\n#define TC_TILE_LOOP if (mask)\n#define TC_MT m\n#endif\n"
             '#define TC_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))\n'
             "// divcall=1 moves the ~20-instruction IEEE division out of line (-18 % SASS); measured on B200 it\n"
             "// is 5-10 % slower than inline division (the call spills live operands), so inline is the default\n"
@@ -293,22 +304,22 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         raise ValueError("warps_per_sm must be a multiple of lockstep, at most 32")
     m = [head, f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n"
                f"#define TC_KMINBLOCKS {warps_per_sm // lockstep}\n"]
-    m += [f"__device__ void {n}(double *__restrict__ m);\n" for n, _ in funcs]
-    m.append("__device__ __noinline__ void tcm_group(int g, double *m, bool p) {\n    switch (g) {\n")
+    m += [f"__device__ void {n}(double *__restrict__ m, unsigned mask);\n" for n, _ in funcs]
+    m.append("__device__ __noinline__ void tcm_group(int g, double *m, unsigned mask) {\n    switch (g) {\n")
     bar = " __syncthreads();" if lockstep > 1 else ""
     for g, calls in enumerate(group_calls):
-        m.append(f"    case {g}:" + "".join(f" if (p) {n}(m);{bar}" for n in calls) + " break;\n")
+        m.append(f"    case {g}:" + "".join(f" {n}(m, mask);{bar}" for n in calls) + " break;\n")
     m.append("    }\n}\n")
-    m.append("__device__ __noinline__ bool tcm_copy(int fn, double *m) {\n    switch (fn) {\n")
+    m.append("__device__ __noinline__ bool tcm_copy(int fn, double *m, unsigned mask) {\n    switch (fn) {\n")
     for fid, calls in copy_calls.items():
-        m.append(f"    case {fid}: " + " ".join(f"{n}(m);" for n in calls) + " return true;\n")
+        m.append(f"    case {fid}: " + " ".join(f"{n}(m, mask);" for n in calls) + " return true;\n")
     m.append("    }\n    return false;\n}\n")
     m.append(f'''#include "tc_kernels.cuh"
 extern "C" {{
 __attribute__((visibility("default"))) int tcm_abi_version(void) {{ return {TCM_ABI}; }}
 __attribute__((visibility("default"))) const char *tcm_fingerprint(void) {{ return "{fp}"; }}
 __attribute__((visibility("default"))) int tcm_image_bytes(void) {{ return (int)sizeof(tc_device_image); }}
-__attribute__((visibility("default"))) int tcm_block(void) {{ return TC_KBLOCK; }}
+__attribute__((visibility("default"))) int tcm_block(void) {{ return TC_KBLOCK * TC_TILES; }}   // instances per CTA
 // force the (lazy) load of the module's device code now rather than inside the first timed solve
 __attribute__((visibility("default"))) int tcm_load(void) {{
     cudaFuncAttributes a;
@@ -319,13 +330,13 @@ __attribute__((visibility("default"))) int tcm_load(void) {{
 // ipmPD_CSsolver() for every instance of the batch: ONE launch, the Newton loop stays on the device
 __attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, double mu0, int maxIter, double aeU,
                                                      double aeEq, int32_t *status, int32_t *iter, void *stream) {{
-    tc_solve_kernel<<<(unsigned)(P->stride / TC_KBLOCK), TC_KBLOCK, 0, (cudaStream_t)stream>>>(
+    tc_solve_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, 0, (cudaStream_t)stream>>>(
         *P, mu0, maxIter, aeU, aeEq, status, iter);
     return (int)cudaGetLastError();
 }}
 // lazy evaluation of the parents of get function fn (classname_getOutputs)
 __attribute__((visibility("default"))) int tcm_eval(const tc_device_image *P, int fn, void *stream) {{
-    tc_eval_kernel<<<(unsigned)(P->stride / TC_KBLOCK), TC_KBLOCK, 0, (cudaStream_t)stream>>>(*P, fn);
+    tc_eval_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, 0, (cudaStream_t)stream>>>(*P, fn);
     return (int)cudaGetLastError();
 }}
 }}

@@ -57,11 +57,11 @@ def test_every_value_read_is_defined(name):
         fns, st = emit_cuda.emit_group(pr, g, ext)
         assert st["loads"] + st["reg_reads"] >= 0
         for _, src in fns:
-            for body in re.split(r"\n\{\n", src)[1:]:
+            for body in re.split(r"TC_TILE_LOOP \{", src)[1:]:
                 defined = set(re.findall(r"double (v\d+)=", body))
                 used = set(re.findall(r"\bv\d+\b", body))
                 assert used <= defined, (g, sorted(used - defined)[:5])
-            stored_slots.update(int(x) // emit_cuda.TILE for x in re.findall(r"\bm\[(\d+)\]=", src))
+            stored_slots.update(int(x) // emit_cuda.TILE for x in re.findall(r"\bmt\[(\d+)\]=", src))
     for i in ext:
         if pr.tab.types[i] not in (it.I_load, it.I_2, it.I_set) and i in pr.group_of:
             assert int(pr.slot[i]) in stored_slots
@@ -80,7 +80,7 @@ def test_module_builds_and_exports_entry_points():
     lib.tcm_fingerprint.restype = ctypes.c_char_p
     assert lib.tcm_fingerprint().decode() == fingerprint(gen.problem)
     assert lib.tcm_abi_version() == emit_cuda.TCM_ABI
-    assert lib.tcm_block() == 32
+    assert lib.tcm_block() == 32      # one warp per CTA, one instance per lane
 
 
 def test_module_path_is_content_addressed():
@@ -88,3 +88,4 @@ def test_module_path_is_content_addressed():
     gen, _ = generated("sls")
     assert module_path(gen) == module_path(gen)
     assert module_path(gen) != module_path(gen, max_loads=44)
+    assert module_path(gen, tiles=2) != module_path(gen, tiles=1)
