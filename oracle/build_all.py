@@ -5,7 +5,8 @@ import sys
 import time
 from concurrent.futures import ProcessPoolExecutor
 
-CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {})]
+CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}),
+           ("mpc_quadcopter", {"T_": 20, "useInertia": True})]   # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
 
 
 def _one(args):

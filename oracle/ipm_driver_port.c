@@ -3,7 +3,7 @@
  * Restatement ("port") of the reference's primal-dual interior-point driver
  * lib/ipmPD_CSsolver.c:132-920 for the option set its C generator can actually emit
  * (lib/cmex2optimizeCS.m:83-93 forces ipmPD_CStimesLambda: skipAffine=1, useLDL=1, large KKT
- * matrix, useInertia=0).  It is #included at the end of the translation unit written by
+ * matrix; useInertia 0 or 1).  It is #included at the end of the translation unit written by
  * oracle/emit_c.py, after the #define table (lib/cmex2optimizeCS.m:303-331) and the generated
  * set/get/copy functions whose names are the reference's `*__` names.
  *
@@ -130,22 +130,46 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
             break;
         }
 
-        if (adjust) {                                            /* :393-548 (useInertia==0) */
+        if (adjust) {                                            /* :393-548 */
             double curv, derr;
+#if useInertia != 0
+            double mp = 0, mn = 0;                               /* read only after being set (:408-419) */
+#endif
             if (updU) { setAddEye2HessianU__(&aeU); updU = 0; }  /* delayed from last iteration */
             if (updEq) { setAddEye2HessianEq__(&aeEq); updEq = 0; }
             getCurvature__(&curv);
+#if useInertia != 0
+            if (curv <= 0) getHessInertia__(&mp, &mn);           /* :408-413 */
+#endif
             getDirectionError__(&derr);
-            if (curv > 0) {                                      /* :415-456 */
+            if (curv > 0
+#if useInertia != 0
+                || (mp == nU && mn == nF + nG)                   /* mpDesired, mnDesired :164-169 */
+#endif
+                ) {                                              /* :415-456 */
                 if (aeU > P_AEMIN && derr < P_MAXDERR) { aeU = p_max(.75 * aeU, P_AEMIN); updU = 1; }
                 if (aeEq > P_AEMIN && derr < P_MAXDERR) { aeEq = p_max(.75 * aeEq, P_AEMIN); updEq = 1; }
                 if (aeU < P_UMAX && derr > P_MAXDERR) { aeU = p_min(10 * aeU, P_UMAX); updU = 1; }
                 if (aeEq < P_EQMAX && derr > P_MAXDERR) { aeEq = p_min(10 * aeEq, P_EQMAX); updEq = 1; }
-            } else if (curv < 0) {                               /* :458-480: one pass, applied now */
+            } else if (curv < 0) {                               /* :458-520: one pass, applied now */
                 int change = 0;
-                if (aeU < P_UMAX) { aeU = p_min(10 * p_max(aeU, P_AEMIN), P_UMAX); setAddEye2HessianU__(&aeU); change = 1; }
-                if (aeEq < P_EQMAX) { aeEq = p_min(10 * p_max(aeEq, P_AEMIN), P_EQMAX); setAddEye2HessianEq__(&aeEq); change = 1; }
-                if (change) { getCurvature__(&curv); getDirectionError__(&derr); }   /* :524-531 */
+#if useInertia == 0
+                const double fU = 10, fEq = 10;
+                const int act = 1;
+#else
+                /* not enough positive eigenvalues: U x10, Eq x2; not enough negative ones: U x2, Eq x10 */
+                const int act = (mp < nU) || (mn < nF + nG);
+                const double fU = (mp < nU) ? 10 : 2, fEq = (mp < nU) ? 2 : 10;
+#endif
+                if (act && aeU < P_UMAX) { aeU = p_min(fU * p_max(aeU, P_AEMIN), P_UMAX); setAddEye2HessianU__(&aeU); change = 1; }
+                if (act && aeEq < P_EQMAX) { aeEq = p_min(fEq * p_max(aeEq, P_AEMIN), P_EQMAX); setAddEye2HessianEq__(&aeEq); change = 1; }
+                if (change) {                                    /* :522-531 */
+                    getCurvature__(&curv);
+#if useInertia != 0
+                    if (curv <= 0) getHessInertia__(&mp, &mn);
+#endif
+                    getDirectionError__(&derr);
+                }
             }
         }
 

@@ -210,7 +210,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     D.gradTolerance = dh[0]; D.addEye2HessianUtolerance = dh[1]; D.equalTolerance = dh[2];
     D.desiredDualityGap = dh[3]; D.alphaMin = dh[4]; D.alphaMax = dh[5];
     D.muFactorAggressive = dh[6]; D.muFactorConservative = dh[7];
-    if (D.useInertia || !D.skipAffine) { tc_destroy(s); return TC_EFORMAT; }
+    if (!D.skipAffine) { tc_destroy(s); return TC_EFORMAT; }   // Mehrotra path: not emitted by cmex2optimizeCS
     s->funcs.assign(funcs, funcs + n_funcs);
     s->set_fids.assign(set_fids, set_fids + n_sets);
     s->out_sizes.assign(out_sizes, out_sizes + n_out);

@@ -53,12 +53,12 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     tc_bT run, updU, updEq, pr, pr2;
     tc_iT status, iter, ls;
     tc_dT aeU, aeEq, mu, muMin, gapTol, alphaMax_, alphaPrimal, alphaDualEq, alphaDualIneq;
-    tc_dT norminf_grad, norminf_eq, gap, ineq, ineq1, dual, v0, v1, v2;
+    tc_dT norminf_grad, norminf_eq, gap, ineq, ineq1, dual, v0, v1, v2, mp, mn;
     TC_FORT {
         run[t] = valid[t]; updU[t] = updEq[t] = false; status[t] = 0; iter[t] = 0; ls[t] = LS_DONE;
         aeU[t] = aeU0; aeEq[t] = aeEq0; mu[t] = mu0; muMin[t] = 0; gapTol[t] = D.desiredDualityGap;
         alphaMax_[t] = D.alphaMax; alphaPrimal[t] = alphaDualEq[t] = alphaDualIneq[t] = 0;
-        norminf_grad[t] = norminf_eq[t] = gap[t] = ineq[t] = ineq1[t] = dual[t] = 0;
+        norminf_grad[t] = norminf_eq[t] = gap[t] = ineq[t] = ineq1[t] = dual[t] = mp[t] = mn[t] = 0;
     }
 
     if (D.setAddEye2Hessian) {                                              // :150-155
@@ -116,7 +116,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             run[t] = false;
         }
 
-        // ---- regularisation control (:393-548, useInertia==0) ----
+        // ---- regularisation control (:393-548) ----
         if (adjust) {
             TC_FORT { pr[t] = run[t] && updU[t]; pr2[t] = run[t] && updEq[t]; }
             tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);            // delayed from last iteration
@@ -124,13 +124,24 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             TC_FORT if (run[t]) updU[t] = updEq[t] = false;
             tc_get(c, P, FN_getCurvature, run);
             tc_value(c, P, FN_getCurvature, 0, run, v0);                    // curvature
+            if (D.useInertia) {                                             // :408-413
+                TC_FORT pr[t] = run[t] && v0[t] <= 0;
+                tc_get(c, P, FN_getHessInertia, pr);
+                tc_value(c, P, FN_getHessInertia, 0, pr, v1);
+                tc_value(c, P, FN_getHessInertia, 1, pr, v2);
+                TC_FORT if (pr[t]) { mp[t] = v1[t]; mn[t] = v2[t]; }
+            }
             tc_get(c, P, FN_getDirectionError, run);
             tc_value(c, P, FN_getDirectionError, 0, run, v1);               // direction error
             TC_FORT {
                 const double curvature = v0[t], derr = v1[t];
                 bool nowU = false, nowEq = false;
+                // inertia of the KKT factor: nU positive, nF+nG negative pivots wanted (:164-169)
+                const bool inertia_ok = D.useInertia && mp[t] == D.nU && mn[t] == D.nF + D.nG;
+                const bool morePos = D.useInertia && mp[t] < D.nU, moreNeg = D.useInertia && mn[t] < D.nF + D.nG;
+                const double fU = (!D.useInertia || morePos) ? 10 : 2, fEq = (!D.useInertia || !morePos) ? 10 : 2;
                 if (run[t]) {
-                    if (curvature > 0) {                                    // :415-456
+                    if (curvature > 0 || inertia_ok) {                      // :415-456
                         if (aeU[t] > TC_addEye2HessianMIN && derr < TC_maxDirectionError) {
                             aeU[t] = TC_MAX(.75 * aeU[t], TC_addEye2HessianMIN);
                             updU[t] = true;
@@ -147,13 +158,13 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
                             aeEq[t] = TC_MIN(10 * aeEq[t], TC_addEye2HessianEqMAX);
                             updEq[t] = true;
                         }
-                    } else if (curvature < 0) {                             // :462-480, single pass
+                    } else if (curvature < 0 && (!D.useInertia || morePos || moreNeg)) {   // :462-520, single pass
                         if (aeU[t] < TC_addEye2HessianUMAX) {
-                            aeU[t] = TC_MIN(10 * TC_MAX(aeU[t], TC_addEye2HessianMIN), TC_addEye2HessianUMAX);
+                            aeU[t] = TC_MIN(fU * TC_MAX(aeU[t], TC_addEye2HessianMIN), TC_addEye2HessianUMAX);
                             nowU = true;
                         }
                         if (aeEq[t] < TC_addEye2HessianEqMAX) {
-                            aeEq[t] = TC_MIN(10 * TC_MAX(aeEq[t], TC_addEye2HessianMIN), TC_addEye2HessianEqMAX);
+                            aeEq[t] = TC_MIN(fEq * TC_MAX(aeEq[t], TC_addEye2HessianMIN), TC_addEye2HessianEqMAX);
                             nowEq = true;
                         }
                     }

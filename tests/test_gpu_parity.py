@@ -13,7 +13,8 @@ from tenscalc_b200 import problems
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_quadcopter", 96, {})]
+CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_quadcopter", 96, {}),
+         ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})]
 
 
 def _oracle(gen, name):
@@ -48,3 +49,49 @@ def test_parity_with_oracle(name, batch, kw, backend):
         assert np.max(np.abs(a - b) / scale) <= 1e-8, k
     print(f"{name}[{backend}]: B={batch} iters {it.min()}..{it.max()} equal_iters={np.array_equal(it, it_o)} "
           f"batch time {t * 1e3:.2f} ms")
+
+
+def _solve(gen, args, P, V, batch, **opts):
+    obj = gen(batch, **opts)
+    for n, _ in gen.parameters:
+        getattr(obj, "setP_" + n)(P[n])
+    for n, _ in gen.variables:
+        getattr(obj, "setV_" + n)(V[n])
+    return obj
+
+
+def test_async_solve_and_two_handles_in_flight():
+    """tc_solve_async on two handles (own stream and scratchbook each) gives the results of tc_solve"""
+    gen, args = generated("sls")
+    batch = 2048
+    P, V = problems.synthetic_inputs("sls", gen, batch, seed=5)
+    ref = _solve(gen, args, P, V, batch)
+    st0, it0, _ = ref.solve(args["mu0"], args["maxIter"], -1)
+    y0 = ref.getOutputs()
+    ref.close()
+    objs = [_solve(gen, args, P, V, batch) for _ in range(2)]
+    res = [(np.full(batch, -1, np.int32), np.full(batch, -1, np.int32)) for _ in objs]
+    for o, (st, it) in zip(objs, res):
+        o.solve_async(st, it, args["mu0"], args["maxIter"])
+    for o, (st, it) in zip(objs, res):
+        y = o.getOutputs()                      # synchronises the handle
+        assert np.array_equal(st, st0) and np.array_equal(it, it0)
+        for a, b in zip(y, y0):
+            assert np.array_equal(a, b)
+        o.close()
+
+
+def test_tiles_option_is_bit_identical():
+    """two instances per lane (emitter option tiles=2) walk the same code: identical results"""
+    gen, args = generated("sls")
+    batch = 1000                                # not a multiple of the CTA size: ragged tail
+    P, V = problems.synthetic_inputs("sls", gen, batch, seed=6)
+    outs = []
+    for opts in ({}, dict(tiles=2)):
+        obj = _solve(gen, args, P, V, batch, **opts)
+        st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+        outs.append((st, it, obj.getOutputs()))
+        obj.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert np.array_equal(a, b)

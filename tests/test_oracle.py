@@ -160,3 +160,23 @@ def test_port_emitter_text_equals_reference_emitter():
         assert a == b
         checked += len(members)
     assert checked > 500
+
+
+def test_inertia_controlled_regularisation_port_equals_reference():
+    """useInertia=true (ipmPD_CSsolver.c:408-519, getHessInertia__ of ipmPD_CStimesLambda.m:244-248):
+    the port driver and the reference's own driver agree bit for bit, and the problem still converges"""
+    from oracle.oracle import Oracle
+    from tenscalc_b200 import problems
+    gen, args = generated("mpc_quadcopter", T_=20, useInertia=True)     # nonconvex: the branch is exercised
+    assert gen.defines["useInertia"] == 1 and "getHessInertia__" in gen.problem.gets
+    P, V = problems.synthetic_inputs("mpc_quadcopter", gen, 64, seed=11)
+    st_r, it_r, out_r, _ = Oracle(gen, "ref").solve_batch(P, V, args["mu0"], args["maxIter"])
+    st_p, it_p, out_p, _ = Oracle(gen, "port").solve_batch(P, V, args["mu0"], args["maxIter"])
+    assert np.array_equal(st_r, st_p) and np.array_equal(it_r, it_p)
+    for k in out_r:
+        assert np.array_equal(out_r[k], out_p[k]), k
+    assert (st_r == 0).mean() > 0.8
+    # and the option matters on this problem: iteration counts differ from the useInertia=false solver
+    gen0, _ = generated("mpc_quadcopter", T_=20)
+    _, it_0, _, _ = Oracle(gen0, "ref").solve_batch(P, V, args["mu0"], args["maxIter"])
+    assert (it_0 != it_r).any()
