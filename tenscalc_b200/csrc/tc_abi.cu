@@ -274,7 +274,16 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     s->module = h;
     s->mod_solve = solve;
     s->mod_eval = eval;
-    return 0;
+    // Warm-up launch over an EMPTY batch (one CTA, every lane invalid: nothing is read or written but
+    // the lanes' own group-status words): the first launch of a module makes the driver size the
+    // local-memory pool for the kernel's stack frames, 0.1-0.3 s that would otherwise be charged to the
+    // first solve.
+    tc_device_image w = s->img;
+    w.batch = 0;
+    w.stride = blk();
+    rc = solve(&w, 1.0, 1, 0.0, 0.0, s->d_status, s->d_iter, (void *)s->stream);
+    if (!rc) rc = (int)cudaStreamSynchronize(s->stream);
+    return rc;
 }
 
 int tc_has_module(const tc_solver *s) { return s ? (s->module != nullptr) : TC_EINVAL; }

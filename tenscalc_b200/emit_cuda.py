@@ -140,7 +140,8 @@ def chunk_group(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_
 
 
 def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
-               max_loads: int = 96, prefetch: int = 1, merge: int = 1) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+               max_loads: int = 96, prefetch: int = 1, merge: int = 1,
+               assume_global: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
     """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics"""
     tab, slot = pr.tab, pr.slot
     members = pr.groups[g]
@@ -197,6 +198,8 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
     for f0 in range(0, len(bodies), merge):
         fname = bodies[f0][0]
         src = [f"__device__ __noinline__ void {fname}(double *__restrict__ m, unsigned mask) {{"]
+        if assume_global:          # LDG/STG instead of generic LD/ST (the pointer's address space is not
+            src.append("__builtin_assume(__isGlobal(m));")   # visible across -rdc translation units)
         for k in range(f0, min(f0 + merge, len(bodies))):
             name, loads, stores, lines = bodies[k]
             # one pass over the chunk's code per tile of the warp: the second pass runs out of the
@@ -251,7 +254,8 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
 
 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
-                warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1):
+                warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1,
+                assume_global: int = 0, resident: int = 0):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
     from .csparse import fingerprint
     from .tape import FN
@@ -262,7 +266,7 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0)
     per_group = []
     for g in range(len(pr.groups)):
-        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge)
+        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global)
         funcs += fs
         group_calls.append([n for n, _ in fs])
         per_group.append(st)
@@ -302,7 +306,10 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         raise ValueError("lockstep must be 1, 2, 4 or 8 warps per CTA")
     if warps_per_sm % lockstep or not 1 <= warps_per_sm <= 32:
         raise ValueError("warps_per_sm must be a multiple of lockstep, at most 32")
-    m = [head, f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n"
+    # `resident` > 0 caps the CTAs resident per SM below the register limit (a dynamic shared-memory
+    # reservation nobody uses): fewer warps in flight = a larger share of the 126 MB L2 per warp
+    smem = 0 if not resident else (227 * 1024 // resident) // 1024 * 1024 - 1024
+    m = [head, f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n#define TC_SMEM_BYTES {smem}\n"
                f"#define TC_KMINBLOCKS {warps_per_sm // lockstep}\n"]
     m += [f"__device__ void {n}(double *__restrict__ m, unsigned mask);\n" for n, _ in funcs]
     m.append("__device__ __noinline__ void tcm_group(int g, double *m, unsigned mask) {\n    switch (g) {\n")
@@ -325,12 +332,14 @@ __attribute__((visibility("default"))) int tcm_load(void) {{
     cudaFuncAttributes a;
     cudaError_t e = cudaFuncGetAttributes(&a, tc_solve_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, tc_eval_kernel);
+    if (e == cudaSuccess && TC_SMEM_BYTES)
+        e = cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     return (int)e;
 }}
 // ipmPD_CSsolver() for every instance of the batch: ONE launch, the Newton loop stays on the device
 __attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, double mu0, int maxIter, double aeU,
                                                      double aeEq, int32_t *status, int32_t *iter, void *stream) {{
-    tc_solve_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, 0, (cudaStream_t)stream>>>(
+    tc_solve_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
         *P, mu0, maxIter, aeU, aeEq, status, iter);
     return (int)cudaGetLastError();
 }}

@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--backend", default="compiled", choices=["compiled", "tape"])
     ap.add_argument("--lockstep", type=int, default=0, help="warps per CTA walking the code together (0: default)")
+    ap.add_argument("--assume-global", type=int, default=0, help="1: __isGlobal assumption -> LDG/STG")
+    ap.add_argument("--prefetch", type=int, default=-1, help="0: no next-chunk L2 prefetch (-1: default)")
+    ap.add_argument("--resident", type=int, default=0, help="cap on resident CTAs per SM (0: register limit)")
     ap.add_argument("--tiles", type=int, default=0, help="instances per lane (0: default)")
     ap.add_argument("--merge", type=int, default=0, help="chunks per emitted function (0: default)")
     ap.add_argument("--divcall", type=int, default=-1, help="1: IEEE division out of line, 0: inline (-1: default)")
@@ -33,7 +36,10 @@ def main():
     gen, sargs = problems.BUILDERS[args.workload]()
     P, V = problems.synthetic_inputs(args.workload, gen, args.batch, seed=7)
     opts = {k: v for k, v in dict(lockstep=args.lockstep, max_loads=args.max_loads,
-                                      warps_per_sm=args.warps_per_sm, merge=args.merge, tiles=args.tiles).items() if v}
+                                      warps_per_sm=args.warps_per_sm, merge=args.merge, tiles=args.tiles,
+                                      assume_global=args.assume_global, resident=args.resident).items() if v}
+    if args.prefetch >= 0:
+        opts["prefetch"] = args.prefetch
     if args.divcall >= 0:
         opts["divcall"] = args.divcall
     obj = gen(args.batch, device=0, backend=args.backend, **opts)
