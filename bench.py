@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--pipeline", type=int, default=3,
                     help="solver handles kept in flight (own stream + scratchbook each): the straggler tail of "
                          "step k overlaps the bulk of steps k+1.. ; 1 = strictly one batch at a time")
+    ap.add_argument("--driver", default="", choices=["", "warp", "lanes"],
+                    help="device driver of the compiled back end (default: the emitter's default)")
     ap.add_argument("--backend", default="compiled", choices=["compiled", "tape"],
                     help="compiled: per-problem sm_100a module (default); tape: generic interpreter")
     return ap.parse_args()
@@ -256,7 +258,8 @@ def run_ours(args, rank, local_rank, world):
     # launches and the few instances that need hundreds of Newton iterations (the tail of one
     # batch) run next to the bulk of the following batches instead of holding the GPU alone
     depth = max(1, min(args.pipeline, K))
-    objs = [gen(B, device=local_rank, backend=args.backend) for _ in range(depth)]
+    mopts = dict(driver=args.driver) if args.driver and args.backend == "compiled" else {}
+    objs = [gen(B, device=local_rank, backend=args.backend, **mopts) for _ in range(depth)]
     obj = objs[0]
     assert obj.has_module() == (args.backend == "compiled")
     exts = [torch.cuda.ExternalStream(o.stream_ptr(), device=torch.device("cuda", local_rank)) for o in objs]

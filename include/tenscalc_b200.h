@@ -99,6 +99,8 @@ int tc_total_newton_steps(tc_solver *s, int64_t *steps); /* sum of iter over the
  * of dependency group g since creation / the last reset.  counts has tc_num_groups entries. */
 int tc_num_groups(const tc_solver *s);
 int tc_group_counts(tc_solver *s, int64_t *counts, int reset);
+/* same, counting WARP-executions: counts[g]*32 / tc_group_counts[g] is the lane occupancy of group g */
+int tc_group_warp_counts(tc_solver *s, int64_t *counts, int reset);
 const char *tc_error_string(int code);
 
 #ifdef __cplusplus

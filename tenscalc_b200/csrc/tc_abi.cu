@@ -188,10 +188,10 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     s->allocs.push_back(d);
     I.group_status = (uint64_t *)d;
     TC_TRY((int)cudaMemsetAsync(d, 0, 2 * s->stride * sizeof(uint64_t), s->stream));
-    TC_TRY((int)cudaMalloc(&d, 128 * sizeof(unsigned long long)));
+    TC_TRY((int)cudaMalloc(&d, 256 * sizeof(unsigned long long)));   // [0,128): instance-, [128,256): warp-executions
     s->allocs.push_back(d);
     I.group_count = (unsigned long long *)d;
-    TC_TRY((int)cudaMemsetAsync(d, 0, 128 * sizeof(unsigned long long), s->stream));
+    TC_TRY((int)cudaMemsetAsync(d, 0, 256 * sizeof(unsigned long long), s->stream));
     TC_TRY((int)cudaMalloc(&d, s->stride * sizeof(int32_t) * 2 + 16));
     s->allocs.push_back(d);
     s->d_status = (int32_t *)d;
@@ -425,16 +425,19 @@ int tc_kernel_launches(const tc_solver *s, int64_t *count) {
 
 int tc_num_groups(const tc_solver *s) { return s ? (int)s->img.n_groups : TC_EINVAL; }
 
-int tc_group_counts(tc_solver *s, int64_t *counts, int reset) {
+static int tc_counts(tc_solver *s, int64_t *counts, int reset, int which) {
     if (!s || !counts) return TC_EINVAL;
     TC_CUDA(cudaSetDevice(s->device));
     unsigned long long h[128];
-    TC_CUDA(cudaMemcpyAsync(h, s->img.group_count, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
-    if (reset) TC_CUDA(cudaMemsetAsync(s->img.group_count, 0, sizeof(h), s->stream));
+    TC_CUDA(cudaMemcpyAsync(h, s->img.group_count + 128 * which, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    if (reset) TC_CUDA(cudaMemsetAsync(s->img.group_count + 128 * which, 0, sizeof(h), s->stream));
     TC_CUDA(cudaStreamSynchronize(s->stream));
     for (int g = 0; g < s->img.n_groups; g++) counts[g] = (int64_t)h[g];
     return 0;
 }
+
+int tc_group_counts(tc_solver *s, int64_t *counts, int reset) { return tc_counts(s, counts, reset, 0); }
+int tc_group_warp_counts(tc_solver *s, int64_t *counts, int reset) { return tc_counts(s, counts, reset, 1); }
 
 int tc_total_newton_steps(tc_solver *s, int64_t *steps) {
     if (!s || !steps) return TC_EINVAL;

@@ -1,7 +1,11 @@
 // Solve / lazy-evaluation kernels shared by the two back ends: the tape interpreter built into
 // libtenscalc_b200.so and the per-problem compiled modules (TC_COMPILED_GROUPS, emit_cuda.py).
 #pragma once
+#ifdef TC_DRIVER_LANES
+#include "tc_driver_lanes.cuh"   // every lane advances through the solver loop on its own (emitter option driver="lanes")
+#else
 #include "tc_driver.cuh"
+#endif
 
 #ifdef TC_COMPILED_GROUPS
 #ifndef TC_LOCKSTEP

@@ -272,7 +272,10 @@ __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image
                 tc_exec_group(c, P.group_start, 64 * w + b, need);
                 // static per-group flop/byte tables x these counts = algorithmic work (the
                 // reference's profiling counters, writeCfunctionpergroup.m:149-177,481-492)
-                if (c.lane == 0 && n) atomicAdd(P.group_count + 64 * w + b, (unsigned long long)n);
+                if (c.lane == 0 && n) {
+                    atomicAdd(P.group_count + 64 * w + b, (unsigned long long)n);
+                    atomicAdd(P.group_count + 128 + 64 * w + b, 1ull);
+                }
             }
 #pragma unroll
             for (int t = 0; t < TC_TILES; t++)

@@ -255,7 +255,7 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
                 warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1,
-                assume_global: int = 0, resident: int = 0):
+                assume_global: int = 0, resident: int = 0, driver: str = "warp"):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
     from .csparse import fingerprint
     from .tape import FN
@@ -309,7 +309,10 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     # `resident` > 0 caps the CTAs resident per SM below the register limit (a dynamic shared-memory
     # reservation nobody uses): fewer warps in flight = a larger share of the 126 MB L2 per warp
     smem = 0 if not resident else (227 * 1024 // resident) // 1024 * 1024 - 1024
-    m = [head, f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n#define TC_SMEM_BYTES {smem}\n"
+    if driver not in ("warp", "lanes") or (driver == "lanes" and (tiles != 1 or lockstep != 1)):
+        raise ValueError("driver must be 'warp' or 'lanes' (lanes: tiles=1, lockstep=1)")
+    m = [head, ("#define TC_DRIVER_LANES 1\n" if driver == "lanes" else ""),
+         f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n#define TC_SMEM_BYTES {smem}\n"
                f"#define TC_KMINBLOCKS {warps_per_sm // lockstep}\n"]
     m += [f"__device__ void {n}(double *__restrict__ m, unsigned mask);\n" for n, _ in funcs]
     m.append("__device__ __noinline__ void tcm_group(int g, double *m, unsigned mask) {\n    switch (g) {\n")

@@ -52,6 +52,7 @@ ABI = [
     ("tc_total_newton_steps", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     ("tc_num_groups", ctypes.c_int, [ctypes.c_void_p]),
     ("tc_group_counts", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    ("tc_group_warp_counts", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     ("tc_error_string", ctypes.c_char_p, [ctypes.c_int]),
 ]
 
@@ -266,6 +267,13 @@ class BatchedSolver:
         return c
 
     # -- measurement hooks -------------------------------------------------------------------------
+    def group_warp_counts(self, reset: bool = False) -> np.ndarray:
+        """warp-executions per dependency group (32*this / group_counts = lanes busy per execution)"""
+        n = self._lib.tc_num_groups(self._h)
+        out = np.zeros(n, dtype=np.int64)
+        _check(self._lib.tc_group_warp_counts(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), int(reset)))
+        return out
+
     def last_solve_ms(self) -> float:
         ms = ctypes.c_float(0)
         _check(self._lib.tc_last_solve_ms(self._h, ctypes.byref(ms)))

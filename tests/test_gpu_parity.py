@@ -13,6 +13,9 @@ from tenscalc_b200 import problems
 
 pytestmark = pytest.mark.gpu
 
+# extra emitter options for the compiled back end, e.g. TC_MODULE_OPTS='{"driver": "lanes"}'
+MODULE_OPTS = __import__("json").loads(__import__("os").environ.get("TC_MODULE_OPTS", "{}"))
+
 CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_quadcopter", 96, {}),
          ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})]
 
@@ -28,7 +31,7 @@ def test_parity_with_oracle(name, batch, kw, backend):
     gen, args = generated(name, **kw)
     P, V = problems.synthetic_inputs(name, gen, batch, seed=1)
     st_o, it_o, out_o, _ = _oracle(gen, name).solve_batch(P, V, args["mu0"], args["maxIter"])
-    obj = gen(batch, backend=backend)
+    obj = gen(batch, backend=backend, **(MODULE_OPTS if backend == "compiled" else {}))
     assert obj.has_module() == (backend == "compiled")
     for n, _ in gen.parameters:
         getattr(obj, "setP_" + n)(P[n])

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--assume-global", type=int, default=0, help="1: __isGlobal assumption -> LDG/STG")
     ap.add_argument("--prefetch", type=int, default=-1, help="0: no next-chunk L2 prefetch (-1: default)")
     ap.add_argument("--resident", type=int, default=0, help="cap on resident CTAs per SM (0: register limit)")
+    ap.add_argument("--driver", default="", help="warp | lanes (default: emitter default)")
     ap.add_argument("--tiles", type=int, default=0, help="instances per lane (0: default)")
     ap.add_argument("--merge", type=int, default=0, help="chunks per emitted function (0: default)")
     ap.add_argument("--divcall", type=int, default=-1, help="1: IEEE division out of line, 0: inline (-1: default)")
@@ -38,6 +39,8 @@ def main():
     opts = {k: v for k, v in dict(lockstep=args.lockstep, max_loads=args.max_loads,
                                       warps_per_sm=args.warps_per_sm, merge=args.merge, tiles=args.tiles,
                                       assume_global=args.assume_global, resident=args.resident).items() if v}
+    if args.driver:
+        opts["driver"] = args.driver
     if args.prefetch >= 0:
         opts["prefetch"] = args.prefetch
     if args.divcall >= 0:
