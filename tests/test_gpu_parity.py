@@ -98,3 +98,24 @@ def test_tiles_option_is_bit_identical():
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     for a, b in zip(outs[0][2], outs[1][2]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,batch,kw", [("sls", 512, {}), ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})])
+def test_lane_decoupled_driver_parity(name, batch, kw):
+    """emitter option driver="lanes" (csrc/tc_driver_lanes.cuh: every lane runs the reference's loop as a
+    coroutine): same status, same iteration counts, same outputs as the CPU oracle"""
+    gen, args = generated(name, **kw)
+    P, V = problems.synthetic_inputs(name, gen, batch, seed=2)
+    st_o, it_o, out_o, _ = _oracle(gen, name).solve_batch(P, V, args["mu0"], args["maxIter"])
+    obj = _solve(gen, args, P, V, batch, driver="lanes")
+    st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+    outs = obj.getOutputs()
+    if not isinstance(outs, dict):
+        outs = {n: o for (n, _), o in zip(gen.outputs, outs)}
+    obj.close()
+    assert np.array_equal(st, st_o) and np.array_equal(it, it_o)
+    ok = st_o == 0
+    for k in out_o:
+        a, b = outs[k][..., ok], out_o[k][..., ok]
+        scale = np.maximum(np.abs(b).max(axis=tuple(range(b.ndim - 1)), keepdims=True), 1e-300)
+        assert np.max(np.abs(a - b) / scale) <= 1e-8, k
