@@ -5,21 +5,28 @@ Counterpart of the reference's C emitter (``writeCinstructionsC``,
 ``lib/@csparse/writeCfunctionpergroup.m:410-443``), re-designed for one-instance-per-lane
 execution on Blackwell:
 
-* every group becomes a sequence of CHUNK functions ``tcg<g>_<k>(double *m)``; ``m`` points at
-  the lane's column of the warp's scratchbook tile, so slot ``s`` of the instance is
-  ``m[32*s]`` and a warp-wide access is one contiguous 256-byte segment (``tc_image.h``);
-* inside a chunk every instruction result is a NAMED LOCAL (a register), every scratchbook
-  operand is loaded once per chunk, and a result is written back to the scratchbook only if
-  somebody outside the chunk reads it (another chunk, another group, a get or a copy) --
-  short-lived temporaries never touch HBM, and ptxas is free to hoist the independent loads
-  of a chunk far ahead of their uses (that is what hides HBM latency at one instance per lane);
+* every group becomes a sequence of CHUNKS; ``merge`` consecutive chunks share one function
+  ``tcg<g>_<k>(double *m, unsigned mask)``.  ``m`` points at the lane's column of the warp's
+  scratchbook tile, so slot ``s`` of the instance is ``m[32*s]`` and a warp-wide access is one
+  contiguous 256-byte segment (``tc_image.h``); ``mask`` says for which of the lane's instances
+  (``tiles`` per lane, normally one) the code runs;
+* a chunk loads ALL its scratchbook operands up front, back to back (at most ``max_loads``
+  distinct ones: they stay in registers), so it pays one memory round trip, and while they are
+  in flight it prefetches the operands of the NEXT chunk into L2 (``prefetch``);
+* inside a chunk every instruction result is a named local (a register) and is written back to
+  the scratchbook only if somebody outside the chunk reads it (another chunk, another group, a
+  get or a copy) -- short-lived temporaries never touch HBM;
 * constants are immediates;
 * the expression of every instruction is the C expression of the reference emitter,
   evaluated in the same order; the translation units are compiled with ``-fmad=false`` so
   multiplies and adds round separately like the reference's x86-64 build.
 
-The chunk size bounds both ptxas' compile time (which is super-linear in the size of a basic
-block) and the register pressure inside a chunk.
+``emit_module`` spreads the functions over part files of equal size (compiled in parallel with
+``-rdc``, objects cached by content) and writes ``main.cu``: the group/copy dispatchers, the
+device-resident solver loop (``csrc/tc_driver.cuh`` or, ``driver="lanes"``,
+``csrc/tc_driver_lanes.cuh``), the kernels and the ``tcm_*`` entry points that
+``tc_attach_module`` binds.  Options and what they measured to on B200 are listed in DESIGN.md
+section 3.1; the defaults are the fastest measured configuration.
 """
 from __future__ import annotations
 
