@@ -202,6 +202,10 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     I.batch = batch;
     I.n_groups = (int32_t)n_groups;
     I.n_consts = (int32_t)n_consts;
+    I.n_funcs = (int32_t)n_funcs;
+    I.m_work = nullptr;
+    I.queue = nullptr;
+    I.work_tiles = 0;
     tc_defines &D = I.def;
     D.nU = (int32_t)ih[16]; D.nG = (int32_t)ih[17]; D.nF = (int32_t)ih[18];
     D.scaleCost = (int32_t)ih[19]; D.scaleInequalities = (int32_t)ih[20]; D.coupledAlphas = (int32_t)ih[21];
@@ -260,6 +264,7 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     auto solve = (decltype(s->mod_solve))dlsym(h, "tcm_solve");
     auto eval = (decltype(s->mod_eval))dlsym(h, "tcm_eval");
     auto load = (int (*)(void))dlsym(h, "tcm_load");
+    auto work = (int (*)(void))dlsym(h, "tcm_work_tiles");   // > 0: work-queue driver, resident warps
     if (!load || !abi || !img || !blk || !fp || !solve || !eval || abi() != TCM_ABI || img() != (int)sizeof(tc_device_image) ||
         blk() <= 0 || s->stride % blk() || (fingerprint && strcmp(fingerprint, fp()))) {
         dlclose(h);
@@ -271,6 +276,26 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
         dlclose(h);
         return rc;
     }
+    if (work && work() > 0) {      // work scratchbook + queue counter of the work-queue driver
+        int64_t tiles = work();
+        if (tiles > s->stride / TC_TILE) tiles = s->stride / TC_TILE;
+        void *d = nullptr;
+        rc = (int)cudaMalloc(&d, (size_t)tiles * (size_t)s->n_slots * TC_TILE * sizeof(double));
+        if (!rc) {
+            s->allocs.push_back(d);
+            s->img.m_work = (double *)d;
+            rc = (int)cudaMalloc(&d, 64);
+        }
+        if (!rc) {
+            s->allocs.push_back(d);
+            s->img.queue = (unsigned long long *)d;
+            s->img.work_tiles = tiles;
+        }
+        if (rc) {
+            dlclose(h);
+            return rc;
+        }
+    }
     s->module = h;
     s->mod_solve = solve;
     s->mod_eval = eval;
@@ -281,7 +306,8 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     tc_device_image w = s->img;
     w.batch = 0;
     w.stride = blk();
-    rc = solve(&w, 1.0, 1, 0.0, 0.0, s->d_status, s->d_iter, (void *)s->stream);
+    if (w.queue) rc = (int)cudaMemsetAsync(w.queue, 0, sizeof(unsigned long long), s->stream);
+    if (!rc) rc = solve(&w, 1.0, 1, 0.0, 0.0, s->d_status, s->d_iter, (void *)s->stream);
     if (!rc) rc = (int)cudaStreamSynchronize(s->stream);
     return rc;
 }
@@ -332,6 +358,7 @@ int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, con
     TC_CUDA(cudaSetDevice(s->device));
     TC_CUDA(cudaEventRecord(s->ev0, s->stream));
     if (s->module) {
+        if (s->img.queue) TC_CUDA(cudaMemsetAsync(s->img.queue, 0, sizeof(unsigned long long), s->stream));
         TC_CUDA((cudaError_t)s->mod_solve(&s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status,
                                           d_iter, (void *)s->stream));
     } else {

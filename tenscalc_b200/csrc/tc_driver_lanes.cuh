@@ -286,98 +286,183 @@ __device__ __noinline__ void tc_lane_resume(tc_lane_state &s, tc_lane &c, const 
             }
             if (adjust && s.aeU > D.addEye2HessianUtolerance) s.status |= 2048;
         }
+#ifdef TC_DRIVER_QUEUE
+        TC_GET(FN_getOutputs);     // the lane's column is recycled: evaluate the outputs before it is
+#endif
     }
     s.pc = -1;
     s.want_kind = TC_WANT_NONE;
 }
 
-__device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &P, const bool (&valid)[1], double mu0,
-                                             int maxIter, double aeU0, double aeEq0, int (&status_out)[1],
-                                             int (&iter_out)[1]) {
-    tc_lane_state s;
-    s.pc = valid[0] ? 0 : -1;
+__device__ __forceinline__ void tc_state_init(tc_lane_state &s, const tc_device_image &P, bool valid, double mu0,
+                                              double aeU0, double aeEq0) {
+    s.pc = valid ? 0 : -1;
     s.want_fn = 0;
     s.want_kind = TC_WANT_NONE;
     s.status = 0; s.iter = 0; s.updU = s.updEq = s.th_grad = s.th_eq = false;
     s.aeU = aeU0; s.aeEq = aeEq0; s.mu = mu0; s.muMin = 0; s.gapTol = P.def.desiredDualityGap;
     s.alphaMax_ = P.def.alphaMax; s.alphaPrimal = s.alphaDualEq = s.alphaDualIneq = 0;
     s.norminf_grad = s.norminf_eq = s.gap = s.ineq = s.ineq1 = s.dual = s.curvature = s.derr = s.mp = s.mn = 0;
-    if (s.pc == 0) tc_lane_resume(s, c, P, mu0, maxIter);
-    __syncwarp();
-    uint32_t big = 0;              // size (tape cells) that makes a group "dominant"
-    for (int g = 0; g < P.n_groups; g++) big = max(big, __ldg(P.group_start + g + 1) - __ldg(P.group_start + g));
-    big = big / 2 + 1;
+}
 
-    while (true) {
-        const bool alive = s.pc >= 0;
-        if (!__any_sync(TC_FULL, alive)) break;
-        // 1. the first group this lane still misses for the function it waits on (128 = none)
-        int front = 128;
-        if (alive) {
-            const tc_func *f = P.funcs + s.want_fn;
-            const uint64_t n0 = f->parents[0] & ~c.st[0][0], n1 = f->parents[1] & ~c.st[0][1];
-            front = n0 ? __ffsll((long long)n0) - 1 : (n1 ? 64 + __ffsll((long long)n1) - 1 : 128);
-        }
-        // 2. lanes whose function is complete go on at once: copies first (one function at a
-        //    time, its code is shared by the lanes that want it), then the solver code up to the
-        //    lane's next get/copy
-        const bool ready = alive && front == 128;
-        if (__any_sync(TC_FULL, ready)) {
-            bool copying = ready && s.want_kind == TC_WANT_COPY;
-            while (__any_sync(TC_FULL, copying)) {
-                const int fn = __shfl_sync(TC_FULL, s.want_fn, __ffs(__ballot_sync(TC_FULL, copying)) - 1);
-                const bool mine = copying && s.want_fn == fn;
+// One scheduling round of the warp: resume the lanes whose function is complete, otherwise run
+// one dependency group.  Must be called by all 32 lanes while any lane is alive (s.pc >= 0).
+__device__ __forceinline__ void tc_lanes_round(tc_lane_state &s, tc_lane &c, const tc_device_image &P, double mu0,
+                                               int maxIter, uint32_t big) {
+    const bool alive = s.pc >= 0;
+    // 1. the first group this lane still misses for the function it waits on (128 = none)
+    int front = 128;
+    if (alive) {
+        const tc_func *f = P.funcs + s.want_fn;
+        const uint64_t n0 = f->parents[0] & ~c.st[0][0], n1 = f->parents[1] & ~c.st[0][1];
+        front = n0 ? __ffsll((long long)n0) - 1 : (n1 ? 64 + __ffsll((long long)n1) - 1 : 128);
+    }
+    // 2. lanes whose function is complete go on at once: copies first (one function at a
+    //    time, its code is shared by the lanes that want it), then the solver code up to the
+    //    lane's next get/copy
+    const bool ready = alive && front == 128;
+    if (__any_sync(TC_FULL, ready)) {
+        bool copying = ready && s.want_kind == TC_WANT_COPY;
+        while (__any_sync(TC_FULL, copying)) {
+            const int fn = __shfl_sync(TC_FULL, s.want_fn, __ffs(__ballot_sync(TC_FULL, copying)) - 1);
+            const bool mine = copying && s.want_fn == fn;
 #ifdef TC_COMPILED_GROUPS
-                const bool done = tcm_copy(fn, c.mb[0], mine ? 1u : 0u);
+            const bool done = tcm_copy(fn, c.mb[0], mine ? 1u : 0u);
 #else
-                const bool done = false;
+            const bool done = false;
 #endif
-                __syncwarp();
-                const tc_func *f = P.funcs + fn;
-                if (!done) {                                                // generic body (uniform)
-                    const uint32_t *io = P.io + f->io_off;
-                    for (uint32_t k = 0; k < f->io_cnt; k += 2) {
-                        const uint32_t d = __ldg(io + k);
-                        const double v = tc_ldop(c, 0, __ldg(io + k + 1), mine);
-                        if (mine) c.mb[0][(size_t)d * TC_TILE] = v;
-                    }
-                }
-                if (mine) {
-                    c.st[0][0] &= ~f->children[0];
-                    c.st[0][1] &= ~f->children[1];
-                    copying = false;
+            __syncwarp();
+            const tc_func *f = P.funcs + fn;
+            if (!done) {                                                    // generic body (uniform)
+                const uint32_t *io = P.io + f->io_off;
+                for (uint32_t k = 0; k < f->io_cnt; k += 2) {
+                    const uint32_t d = __ldg(io + k);
+                    const double v = tc_ldop(c, 0, __ldg(io + k + 1), mine);
+                    if (mine) c.mb[0][(size_t)d * TC_TILE] = v;
                 }
             }
-            if (ready) tc_lane_resume(s, c, P, mu0, maxIter);
-            __syncwarp();
-            continue;
+            if (mine) {
+                c.st[0][0] &= ~f->children[0];
+                c.st[0][1] &= ~f->children[1];
+                copying = false;
+            }
         }
-        // 3. nobody can go on: run ONE group.  Cheap groups: the front group of the lane that is
-        //    furthest behind (keeps the lanes together, like a warp-synchronous walk).  The
-        //    dominant group (the KKT factorisation; >= half the largest group's size) is a
-        //    RENDEZVOUS: it runs only when every living lane is waiting for a dominant group, so a
-        //    lane that re-factorises within an iteration shares the pass with the others' next one.
-        const int fg = alive ? front : 0;
-        const bool held = alive && (__ldg(P.group_start + fg + 1) - __ldg(P.group_start + fg)) >= big;
-        const bool some_free = __any_sync(TC_FULL, alive && !held);     // (a vote: outside any short-circuit)
-        const bool cand = alive && (!held || !some_free);
-        unsigned long long key = cand ? ((unsigned long long)(((unsigned)s.iter << 16) | ((unsigned)s.pc & 0xffffu)) << 5) | c.lane
-                                      : ~0ull;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(TC_FULL, key, o);
-            key = other < key ? other : key;
-        }
-        const int g = __shfl_sync(TC_FULL, front, (int)(key & 31u));
-        const bool need[1] = {front == g};
-        tc_exec_group(c, P.group_start, g, need);
-        if (need[0]) c.st[0][g >> 6] |= 1ull << (g & 63);
-        const unsigned vote = __ballot_sync(TC_FULL, need[0]);
-        if (c.lane == 0) {
-            atomicAdd(P.group_count + g, (unsigned long long)__popc(vote));
-            atomicAdd(P.group_count + 128 + g, 1ull);
-        }
+        if (ready) tc_lane_resume(s, c, P, mu0, maxIter);
+        __syncwarp();
+        return;
     }
+    // 3. nobody can go on: run ONE group.  Cheap groups: the front group of the lane that is
+    //    furthest behind (keeps the lanes together, like a warp-synchronous walk).  The
+    //    dominant group (the KKT factorisation; >= half the largest group's size) is a
+    //    RENDEZVOUS: it runs only when every living lane is waiting for a dominant group, so a
+    //    lane that re-factorises within an iteration shares the pass with the others' next one.
+    const int fg = alive ? front : 0;
+    const bool held = alive && (__ldg(P.group_start + fg + 1) - __ldg(P.group_start + fg)) >= big;
+    const bool some_free = __any_sync(TC_FULL, alive && !held);         // (a vote: outside any short-circuit)
+    const bool cand = alive && (!held || !some_free);
+    unsigned long long key = cand ? ((unsigned long long)(((unsigned)s.iter << 16) | ((unsigned)s.pc & 0xffffu)) << 5) | c.lane
+                                  : ~0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(TC_FULL, key, o);
+        key = other < key ? other : key;
+    }
+    const int g = __shfl_sync(TC_FULL, front, (int)(key & 31u));
+    const bool need[1] = {front == g};
+    tc_exec_group(c, P.group_start, g, need);
+    if (need[0]) c.st[0][g >> 6] |= 1ull << (g & 63);
+    const unsigned vote = __ballot_sync(TC_FULL, need[0]);
+    if (c.lane == 0) {
+        atomicAdd(P.group_count + g, (unsigned long long)__popc(vote));
+        atomicAdd(P.group_count + 128 + g, 1ull);
+    }
+}
+
+__device__ __forceinline__ uint32_t tc_dominant_size(const tc_device_image &P) {
+    uint32_t big = 0;              // size (tape cells) that makes a group "dominant"
+    for (int g = 0; g < P.n_groups; g++) big = max(big, __ldg(P.group_start + g + 1) - __ldg(P.group_start + g));
+    return big / 2 + 1;
+}
+
+__device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &P, const bool (&valid)[1], double mu0,
+                                             int maxIter, double aeU0, double aeEq0, int (&status_out)[1],
+                                             int (&iter_out)[1]) {
+    tc_lane_state s;
+    tc_state_init(s, P, valid[0], mu0, aeU0, aeEq0);
+    if (s.pc == 0) tc_lane_resume(s, c, P, mu0, maxIter);
+    __syncwarp();
+    const uint32_t big = tc_dominant_size(P);
+    while (__any_sync(TC_FULL, s.pc >= 0)) tc_lanes_round(s, c, P, mu0, maxIter, big);
     status_out[0] = s.status;
     iter_out[0] = s.iter;
 }
+
+#ifdef TC_DRIVER_QUEUE
+// WORK-QUEUE form (emitter option driver="queue"): the grid is one warp per resident slot; every
+// lane works in its own column of a WORK scratchbook (P.m_work) and takes instances from a
+// global counter.  Taking an instance = copying the slots of its set functions from the instance's
+// column of the batch scratchbook; finishing = writing status/iter, copying the output slots back
+// and marking the output groups valid there (tc_get_outputs then gathers without recomputing).
+// Lanes are refilled when TC_REFILL_MIN of a warp are idle (their start-up groups then run for
+// several lanes at once) or when the warp has nothing else to do.
+#ifndef TC_REFILL_MIN
+#define TC_REFILL_MIN 8
+#endif
+
+__device__ __forceinline__ void tc_queue_solve(tc_lane &c, const tc_device_image &P, double mu0, int maxIter,
+                                               double aeU0, double aeEq0, int32_t *__restrict__ status,
+                                               int32_t *__restrict__ iter) {
+    tc_lane_state s;
+    tc_state_init(s, P, false, mu0, aeU0, aeEq0);
+    long long inst = -1;           // the instance this lane is working on
+    bool exhausted = false;        // the queue had nothing left for this lane
+    const uint32_t big = tc_dominant_size(P);
+    const tc_func *fo = P.funcs + FN_getOutputs;
+    while (true) {
+        // a lane whose solver loop ended hands its instance back
+        const bool finished = s.pc < 0 && inst >= 0;
+        if (__any_sync(TC_FULL, finished)) {
+            if (finished) {
+                status[inst] = s.status;
+                iter[inst] = s.iter;
+                P.group_status[inst] = fo->parents[0];
+                P.group_status[P.stride + inst] = fo->parents[1];
+            }
+            for (uint32_t k = 0; k < fo->io_cnt; k++) {                     // uniform loop, per-lane targets
+                const uint32_t w = __ldg(P.io + fo->io_off + k);
+                if (finished && w != TC_NO_SLOT && !(w & TC_CONST_BIT))
+                    TC_M(P, w, inst) = c.mb[0][(size_t)w * TC_TILE];
+            }
+            if (finished) inst = -1;
+        }
+        const bool idle = s.pc < 0 && !exhausted;
+        const unsigned idle_mask = __ballot_sync(TC_FULL, idle);
+        const bool any_alive = __any_sync(TC_FULL, s.pc >= 0);
+        if (idle_mask && (__popc(idle_mask) >= TC_REFILL_MIN || !any_alive)) {
+            unsigned long long base = 0;
+            if (c.lane == 0) base = atomicAdd(P.queue, (unsigned long long)__popc(idle_mask));
+            base = __shfl_sync(TC_FULL, base, 0);
+            const long long j = (long long)base + __popc(idle_mask & ((1u << c.lane) - 1u));
+            const bool take = idle && j < P.batch;
+            if (idle && !take) exhausted = true;
+            for (int fn = FN_USER0; fn < P.n_funcs; fn++) {                 // <class>_set_* of the new instance
+                const tc_func *f = P.funcs + fn;
+                for (uint32_t k = 0; k < f->io_cnt; k++) {
+                    const uint32_t slot = __ldg(P.io + f->io_off + k);
+                    if (take) c.mb[0][(size_t)slot * TC_TILE] = TC_M(P, slot, j);
+                }
+            }
+            if (take) {
+                inst = j;
+                c.st[0][0] = c.st[0][1] = 0;                                // every group is stale for the new instance
+                tc_state_init(s, P, true, mu0, aeU0, aeEq0);
+                tc_lane_resume(s, c, P, mu0, maxIter);
+            }
+            __syncwarp();
+            continue;
+        }
+        if (!any_alive) break;     // nothing running, nothing left to take
+        tc_lanes_round(s, c, P, mu0, maxIter, big);
+    }
+}
+#endif  // TC_DRIVER_QUEUE

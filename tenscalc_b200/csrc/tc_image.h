@@ -87,6 +87,12 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     int32_t n_groups;
     int32_t n_consts;
     tc_defines def;
+    // work-queue driver (emitter option driver="queue"; NULL/0 otherwise)
+    double *m_work;               // [work_tiles][n_slots][32]: one column per RESIDENT lane
+    unsigned long long *queue;    // next instance to hand out (reset before every solve)
+    int64_t work_tiles;
+    int32_t n_funcs;              // funcs[FN_USER0 .. n_funcs) are the user set functions
+    int32_t pad_;
 };
 
 // address of scratchbook slot `slot` of instance `inst`

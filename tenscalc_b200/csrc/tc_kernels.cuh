@@ -60,6 +60,23 @@ __device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device
     }
 }
 
+#ifdef TC_DRIVER_QUEUE
+// whole solve of ipmPD_CSsolver() for every instance of the batch by a grid of RESIDENT warps that
+// pull instances from a queue (tc_driver_lanes.cuh); one launch per tc_solve
+__global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
+                                                            double aeU, double aeEq,
+                                                            int32_t *__restrict__ status,
+                                                            int32_t *__restrict__ iter) {
+    tc_lane c;
+    c.sm = nullptr;
+    c.consts = P.consts;
+    c.tape = P.tape;
+    c.lane = threadIdx.x & 31u;
+    c.mb[0] = P.m_work + ((size_t)blockIdx.x * (size_t)P.n_slots) * TC_TILE + c.lane;
+    c.st[0][0] = c.st[0][1] = 0;
+    tc_queue_solve(c, P, mu0, maxIter, aeU, aeEq, status, iter);
+}
+#else
 // whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
 __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
                                                             double aeU, double aeEq,
@@ -80,6 +97,8 @@ __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_solve_kernel(tc_d
             iter[tc_inst(t)] = it[t];
         }
 }
+
+#endif  // TC_DRIVER_QUEUE
 
 // lazy evaluation of the parents of one get function (classname_getOutputs)
 __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_eval_kernel(tc_device_image P, int fn) {

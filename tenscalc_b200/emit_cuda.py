@@ -316,9 +316,10 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     # `resident` > 0 caps the CTAs resident per SM below the register limit (a dynamic shared-memory
     # reservation nobody uses): fewer warps in flight = a larger share of the 126 MB L2 per warp
     smem = 0 if not resident else (227 * 1024 // resident) // 1024 * 1024 - 1024
-    if driver not in ("warp", "lanes") or (driver == "lanes" and (tiles != 1 or lockstep != 1)):
-        raise ValueError("driver must be 'warp' or 'lanes' (lanes: tiles=1, lockstep=1)")
-    m = [head, ("#define TC_DRIVER_LANES 1\n" if driver == "lanes" else ""),
+    if driver not in ("warp", "lanes", "queue") or (driver != "warp" and (tiles != 1 or lockstep != 1)):
+        raise ValueError("driver must be 'warp', 'lanes' or 'queue' (lanes/queue: tiles=1, lockstep=1)")
+    m = [head, ("#define TC_DRIVER_LANES 1\n" if driver != "warp" else ""),
+         ("#define TC_DRIVER_QUEUE 1\n" if driver == "queue" else ""),
          f"#define TC_COMPILED_GROUPS 1\n#define TC_LOCKSTEP {lockstep}\n#define TC_SMEM_BYTES {smem}\n"
                f"#define TC_KMINBLOCKS {warps_per_sm // lockstep}\n"]
     m += [f"__device__ void {n}(double *__restrict__ m, unsigned mask);\n" for n, _ in funcs]
@@ -337,6 +338,17 @@ __attribute__((visibility("default"))) int tcm_abi_version(void) {{ return {TCM_
 __attribute__((visibility("default"))) const char *tcm_fingerprint(void) {{ return "{fp}"; }}
 __attribute__((visibility("default"))) int tcm_image_bytes(void) {{ return (int)sizeof(tc_device_image); }}
 __attribute__((visibility("default"))) int tcm_block(void) {{ return TC_KBLOCK * TC_TILES; }}   // instances per CTA
+// work-queue driver: number of resident warps = tiles of the work scratchbook (0: other drivers)
+__attribute__((visibility("default"))) int tcm_work_tiles(void) {{
+#ifdef TC_DRIVER_QUEUE
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms * TC_KMINBLOCKS;
+#else
+    return 0;
+#endif
+}}
 // force the (lazy) load of the module's device code now rather than inside the first timed solve
 __attribute__((visibility("default"))) int tcm_load(void) {{
     cudaFuncAttributes a;
@@ -349,7 +361,8 @@ __attribute__((visibility("default"))) int tcm_load(void) {{
 // ipmPD_CSsolver() for every instance of the batch: ONE launch, the Newton loop stays on the device
 __attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, double mu0, int maxIter, double aeU,
                                                      double aeEq, int32_t *status, int32_t *iter, void *stream) {{
-    tc_solve_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
+    const unsigned grid = P->queue ? (unsigned)P->work_tiles : (unsigned)(P->stride / (TC_KBLOCK * TC_TILES));
+    tc_solve_kernel<<<grid, TC_KBLOCK, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
         *P, mu0, maxIter, aeU, aeEq, status, iter);
     return (int)cudaGetLastError();
 }}

@@ -100,14 +100,16 @@ def test_tiles_option_is_bit_identical():
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("name,batch,kw", [("sls", 512, {}), ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})])
-def test_lane_decoupled_driver_parity(name, batch, kw):
+@pytest.mark.parametrize("driver", ["lanes", "queue"])
+@pytest.mark.parametrize("name,batch,kw", [("sls", 5000, {}), ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})])
+def test_lane_decoupled_driver_parity(name, batch, kw, driver):
     """emitter option driver="lanes" (csrc/tc_driver_lanes.cuh: every lane runs the reference's loop as a
-    coroutine): same status, same iteration counts, same outputs as the CPU oracle"""
+    coroutine) and driver="queue" (the same, with resident warps pulling instances from a work queue into
+    a work scratchbook): same status, same iteration counts, same outputs as the CPU oracle"""
     gen, args = generated(name, **kw)
     P, V = problems.synthetic_inputs(name, gen, batch, seed=2)
     st_o, it_o, out_o, _ = _oracle(gen, name).solve_batch(P, V, args["mu0"], args["maxIter"])
-    obj = _solve(gen, args, P, V, batch, driver="lanes")
+    obj = _solve(gen, args, P, V, batch, driver=driver)
     st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
     outs = obj.getOutputs()
     if not isinstance(outs, dict):
