@@ -9,21 +9,28 @@ CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}
            ("mpc_quadcopter", {"T_": 20, "useInertia": True})]   # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
 
 
+# extra builds of the benchmark workload: the toolbox's default -O0 and -O2 beside the headline -O1
+# (bench.py cpu_baseline.other_opt_levels), and the libm-sensitivity probe (bench.py parity.libm_noise_floor)
+EXTRA = [("mpc_quadcopter", {}, "-O0", ""), ("mpc_quadcopter", {}, "-O2", ""), ("mpc_quadcopter", {}, "-O1", "crpow")]
+
+
 def _one(args):
-    name, kw, kind = args
+    name, kw, kind, opt, variant = args
     from tenscalc_b200 import problems
     from oracle.oracle import Oracle
     gen, _ = problems.BUILDERS[name](**kw)
     t = time.time()
-    so = Oracle(gen, kind).build()
-    return name, kind, so, time.time() - t
+    so = Oracle(gen, kind, opt, variant=variant).build()
+    return name, kind + opt + variant, so, time.time() - t
 
 
-def build_all(kinds=("ref", "port"), configs=CONFIGS, workers=4):
-    jobs = [(n, kw, k) for n, kw in configs for k in kinds]
+def build_all(kinds=("ref", "port"), configs=CONFIGS, workers=4, extra=True):
+    jobs = [(n, kw, k, "-O1", "") for n, kw in configs for k in kinds]
+    if extra:
+        jobs += [(n, kw, kinds[0], opt, var) for n, kw, opt, var in EXTRA]
     with ProcessPoolExecutor(workers) as ex:
         for name, kind, so, dt in ex.map(_one, jobs):
-            print(f"oracle {name:16s} {kind:5s} {dt:6.1f}s  {so}")
+            print(f"oracle {name:16s} {kind:12s} {dt:6.1f}s  {so}")
 
 
 if __name__ == "__main__":

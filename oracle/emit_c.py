@@ -185,6 +185,18 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
     w("/* generated by oracle/emit_c.py -- CPU oracle, test infrastructure only */\n")
     w("#include <math.h>\n#include <float.h>\n#include <string.h>\n#include <stdint.h>\n#include <stdlib.h>\n")
     w("#define SCRATCHBOOK_TYPE double\n#define EXPORT __attribute__((visibility(\"default\")))\n")
+    # libm-sensitivity probe (Oracle(..., variant="crpow"), built with -DORACLE_CRPOW): the CORRECTLY ROUNDED
+    # x^-1/2 and x^-3/2 in place of glibc's pow, which differs from them on ~8e-4 of arguments.  Comparing the
+    # two oracles on the same batch measures how many instances change iteration count when ONE libm result in
+    # a thousand moves by one ULP -- the noise floor of any parity claim on problems that call pow.
+    w("#ifdef ORACLE_CRPOW\n"
+      "static void oracle_rsqrt_dd(double x,double *hi,double *lo){double r=1.0/sqrt(x),t=r*r,tl=fma(r,r,-t),s=x*t,\n"
+      "  sl=fma(x,t,-s)+x*tl,e=(1.0-s)-sl; *hi=r; *lo=0.5*r*e;}\n"
+      "static double oracle_crpow(double x,double y){double h,l;\n"
+      "  if (y==-.5 && x>1e-290 && x<1e290){oracle_rsqrt_dd(x,&h,&l); return h+l;}\n"
+      "  if (y==-1.5 && x>1e-190 && x<1e190){oracle_rsqrt_dd(x,&h,&l); double q0=h/x,rem=fma(-q0,x,h); return q0+(rem+l)/x;}\n"
+      "  return pow(x,y);}\n"
+      "#define pow(x,y) oracle_crpow(x,y)\n#endif\n")
     for k, v in pr.defines.items():
         w(f"#define {k} {v:e}\n" if k in _DOUBLE_DEFINES else f"#define {k} {v}\n")
     w(f"static SCRATCHBOOK_TYPE scratchbook[{max(pr.n_slots, 1)}];\n")

@@ -49,7 +49,8 @@ def unpack_outputs(gen: GeneratedSolver, Y: np.ndarray):
 
 
 class Oracle:
-    def __init__(self, gen: GeneratedSolver, kind: str = "ref", opt: str = "-O1", tag: Optional[str] = None):
+    def __init__(self, gen: GeneratedSolver, kind: str = "ref", opt: str = "-O1", tag: Optional[str] = None,
+                 variant: str = ""):
         self.gen = gen
         self.kind = kind
         os.makedirs(OUT, exist_ok=True)
@@ -58,7 +59,11 @@ class Oracle:
             from tenscalc_b200.csparse import fingerprint
             tag = gen.classname + "_" + fingerprint(gen.problem)[:10]
         self.opt = opt
-        self.so = os.path.join(OUT, f"{tag}_{kind}{opt.replace('-', '_')}.so")
+        if variant not in ("", "crpow"):
+            raise ValueError("variant must be '' or 'crpow' (libm-sensitivity probe, see emit_c.py)")
+        self.variant = variant
+        self.so = os.path.join(OUT, f"{tag}_{kind}{opt.replace('-', '_').replace(' ', '').replace('=', '')}"
+                                    f"{'_' + variant if variant else ''}.so")
         self.lib = None
 
     def build(self, force: bool = False) -> str:
@@ -71,7 +76,8 @@ class Oracle:
         with open(cfile, "w") as f:
             f.write(src)
         # plain gcc, no -march/-ffast-math: the reference is built the same way by CmexTools
-        subprocess.check_call(["gcc", self.opt, "-w", "-shared", "-fPIC", "-fvisibility=hidden",
+        extra = ["-DORACLE_CRPOW", "-mfma", "-ffp-contract=off"] if self.variant == "crpow" else []
+        subprocess.check_call(["gcc"] + self.opt.split() + extra + ["-w", "-shared", "-fPIC", "-fvisibility=hidden",
                                cfile, "-o", self.so, "-lm"])
         return self.so
 

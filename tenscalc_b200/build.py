@@ -37,6 +37,26 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_colamd(force: bool = False) -> str:
+    """``tenscalc_b200/_gen/libcolamd.so``: COLAMD (``symamd_l``) compiled, where they lie, from the
+    sources of a SuiteSparse tree -- ``TENSCALC_SUITESPARSE`` or the reference's vendored submodule --
+    the third-party library behind MATLAB's ``symamd`` that ``sparsity_ldl.m:91`` calls.  Returns ""
+    when no SuiteSparse tree is present (``ordering.symamd`` then uses its committed cache)."""
+    from .ordering import COLAMD_LIB
+    root = os.environ.get("TENSCALC_SUITESPARSE", "/root/reference/SuiteSparse")
+    src = os.path.join(root, "COLAMD", "Source", "colamd.c")
+    if not os.path.exists(src):
+        return COLAMD_LIB if os.path.exists(COLAMD_LIB) else ""
+    if force or not os.path.exists(COLAMD_LIB):
+        os.makedirs(os.path.dirname(COLAMD_LIB), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-w", "-shared", "-fPIC", "-DDLONG",
+                               "-I" + os.path.join(root, "COLAMD", "Include"),
+                               "-I" + os.path.join(root, "SuiteSparse_config"), src,
+                               os.path.join(root, "SuiteSparse_config", "SuiteSparse_config.c"),
+                               "-o", COLAMD_LIB, "-lm"])
+    return COLAMD_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
 

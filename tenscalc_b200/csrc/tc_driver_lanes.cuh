@@ -193,8 +193,10 @@ __device__ __noinline__ void tc_lane_resume(tc_lane_state &s, tc_lane &c, const 
                     TC_GET(FN_getMinF_s);
                     s.ineq1 = TC_VAL(FN_getMinF_s, 0);                      // recheck just inside
                 }
-                // accepted iff ineq>0 and ineq1>ineq/10 (state only: no local may live across an await)
-                if (!(s.ineq > 0 && s.ineq1 > s.ineq / 10)) {
+                // :704,716 as written in the reference (a NaN in the re-check keeps the step): try the smallest
+                // step iff ineq<=0 or ineq1<=ineq/10.  ineq1 is only meaningful when ineq>0 (state only: no
+                // local may live across an await)
+                if (s.ineq <= 0 || s.ineq1 <= s.ineq / 10) {
                     s.alphaPrimal = D.alphaMin / TC_stepback;               // try the smallest step :716-749
                     TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
                     TC_GET(FN_getMinF_s);
@@ -418,6 +420,7 @@ __device__ __forceinline__ void tc_queue_solve(tc_lane &c, const tc_device_image
     bool exhausted = false;        // the queue had nothing left for this lane
     const uint32_t big = tc_dominant_size(P);
     const tc_func *fo = P.funcs + FN_getOutputs;
+    const tc_func *fu = P.funcs + FN_updatePrimalDual;   // io = (dst,src) pairs: dst = u, nu, lambda
     while (true) {
         // a lane whose solver loop ended hands its instance back
         const bool finished = s.pc < 0 && inst >= 0;
@@ -432,6 +435,12 @@ __device__ __forceinline__ void tc_queue_solve(tc_lane &c, const tc_device_image
                 const uint32_t w = __ldg(P.io + fo->io_off + k);
                 if (finished && w != TC_NO_SLOT && !(w & TC_CONST_BIT))
                     TC_M(P, w, inst) = c.mb[0][(size_t)w * TC_TILE];
+            }
+            // the optimum itself (u, nu, lambda) goes back too: a later set_<parameter> + getOutputs without a
+            // new solve re-evaluates the output groups on the batch scratchbook, like the reference does
+            for (uint32_t k = 0; k < fu->io_cnt; k += 2) {
+                const uint32_t w = __ldg(P.io + fu->io_off + k);
+                if (finished) TC_M(P, w, inst) = c.mb[0][(size_t)w * TC_TILE];
             }
             if (finished) inst = -1;
         }

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include "tc_image.h"
+#include "tc_math.cuh"
 
 #define TC_FULL 0xFFFFFFFFu
 
@@ -85,8 +86,8 @@ __device__ __forceinline__ double tc_unary(int op, double x) {
     case I_abs: return fabs(x);
     case I_sign: return (x >= 0) ? 1.0 : -1.0;
     case I_sqrt: return sqrt(x);
-    case I_Dsqrt: return __dmul_rn(.5, pow(x, -.5));
-    case I_DDsqrt: return __dmul_rn(-.25, pow(x, -1.5));
+    case I_Dsqrt: return __dmul_rn(.5, tc_pow_m05(x));
+    case I_DDsqrt: return __dmul_rn(-.25, tc_pow_m15(x));
     case I_sqr: return __dmul_rn(x, x);
     case I_2times: return __dmul_rn(2.0, x);
     case I_cube: return __dmul_rn(__dmul_rn(x, x), x);

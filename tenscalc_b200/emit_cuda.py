@@ -91,7 +91,7 @@ def expression(t: int, p: Sequence[float], o: List[str], r: str) -> str:
         it.I_round: f"round({x})", it.I_ceil: f"ceil({x})", it.I_floor: f"floor({x})",
         it.I_abs: f"fabs({x})", it.I_sign: f"({x}>=0)?1.0:-1.0", it.I_2times: f"2.0*{x}",
         it.I_6times: f"6.0*{x}", it.I_sqr: f"{x}*{x}", it.I_3sqr: f"3.0*{x}*{x}", it.I_cube: f"{x}*{x}*{x}",
-        it.I_sqrt: f"sqrt({x})", it.I_Dsqrt: f".5*pow({x},-.5)", it.I_DDsqrt: f"-.25*pow({x},-1.5)",
+        it.I_sqrt: f"sqrt({x})", it.I_Dsqrt: f".5*tc_pow_m05({x})", it.I_DDsqrt: f"-.25*tc_pow_m15({x})",
         it.I_inv: f"1.0/{x}", it.I_minus_inv_sqr: f"-1.0/({x}*{x})", it.I_2_inv_cube: f"2.0/({x}*{x}*{x})",
         it.I_cos: f"cos({x})", it.I_minus_cos: f"-cos({x})", it.I_sin: f"sin({x})",
         it.I_minus_sin: f"-sin({x})", it.I_log: f"log({x})", it.I_exp: f"exp({x})", it.I_atan: f"atan({x})",
@@ -288,7 +288,7 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     # part files of roughly equal size (ptxas time is what we balance)
     if tiles not in (1, 2, 4, 8):
         raise ValueError("tiles must be 1, 2, 4 or 8 instances per lane")
-    head = ("// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n"
+    head = ("// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n#include \"tc_math.cuh\"\n"
             f"#define TC_TILES {tiles}\n#define TC_TILE_STRIDE {int(pr.n_slots) * TILE}ull\n"
             "#if TC_TILES > 1\n"
             '#define TC_TILE_LOOP _Pragma("unroll 1") for (int t = 0; t < TC_TILES; t++) if ((mask >> t) & 1u)\n'

@@ -115,7 +115,7 @@ def build_ipm_timeslambda(code: CSparse, u: List[int], f: Id, F: List[Id], G: Li
             Ftl = tab.dot((F_u[k][i], lam[k]) for k in range(nF) if i in F_u[k])
             b0.append(tab.add([(1, Ftl), (-1, f_u.get(i))]))
         b0 += [None] * nG
-        fac0 = ldlmod.ldl(tab, WW0, ordering(WW0) if ordering else None)
+        fac0 = ldlmod.ldl(tab, WW0, ordering)
         wnu0 = ldlmod.solve(tab, fac0, b0)
         zero = tab.append_unique(it.I_load, (0.0,))
         code.declare_copy("initDualEqX__", nu, [zero if x is None else x for x in wnu0[nU:]])
@@ -151,7 +151,7 @@ def build_ipm_timeslambda(code: CSparse, u: List[int], f: Id, F: List[Id], G: Li
             WW[r][i] = x
             WW[i][r] = x
         WW[r][r] = tab.neg(tab.mul([F[k], lam[k]]))
-    fac = ldlmod.ldl(tab, WW, ordering(WW) if ordering else None)
+    fac = ldlmod.ldl(tab, WW, ordering)
     out["factor"] = fac
 
     # inertia (:244-248)

@@ -6,10 +6,11 @@ pivoting, symbolic fill) and of ``sparsity_mldivide_l1.m:66-102`` /
 ``sparsity_mldivide_d.m:60-74`` / ``sparsity_mldivide_u1.m:67-104`` (permute b,
 forward substitution, divide by D, backward substitution, inverse permutation).
 
-Ordering: the reference calls MATLAB's ``symamd(A,[1000,0])`` (sparsity_ldl.m:91),
-which is not available offline; a greedy minimum-degree ordering on the elimination
-graph is used instead.  Any symmetric ordering is admissible for the quasi-definite
-KKT matrices assembled in ``ipm_builder`` -- only fill, not correctness, depends on it.
+Ordering: the reference calls MATLAB's ``symamd(A,[1000,0])`` (sparsity_ldl.m:91); so does
+this module by default (``ordering.py``: COLAMD's ``symamd_l`` with the same knobs, committed
+permutation cache for boxes without the SuiteSparse sources).  Any symmetric ordering is
+admissible for the quasi-definite KKT matrices assembled in ``ipm_builder`` -- only fill, not
+correctness, depends on it -- and ``order`` may name another method or be an explicit permutation.
 """
 from __future__ import annotations
 
@@ -20,36 +21,8 @@ from .itable import InstructionTable, Id
 SparseSym = List[Dict[int, int]]  # rows[i] = {j: instruction}  (full symmetric pattern)
 
 
-def minimum_degree_ordering(pattern: List[set]) -> List[int]:
-    """Greedy minimum degree on the elimination graph (exact degree update).
-
-    ``pattern[i]`` = set of j!=i with A(i,j) structurally non-zero (symmetric).
-    Ties are broken by the original index so that the ordering is deterministic.
-    """
-    import heapq
-
-    n = len(pattern)
-    adj = [set(s) - {i} for i, s in enumerate(pattern)]
-    alive = [True] * n
-    heap = [(len(adj[i]), i) for i in range(n)]
-    heapq.heapify(heap)
-    order: List[int] = []
-    while heap:
-        d, v = heapq.heappop(heap)
-        if not alive[v] or d != len(adj[v]):
-            continue
-        alive[v] = False
-        order.append(v)
-        nb = adj[v]
-        for a in nb:
-            s = adj[a]
-            s.discard(v)
-            s |= nb
-            s.discard(a)
-        for a in nb:
-            heapq.heappush(heap, (len(adj[a]), a))
-        adj[v] = set()
-    return order
+from .ordering import minimum_degree as minimum_degree_ordering  # noqa: E402,F401  (round-1 name)
+from . import ordering as _ordering  # noqa: E402
 
 
 class LDLFactor:
@@ -63,18 +36,16 @@ class LDLFactor:
         return sum(len(r) for r in self.L) + self.n
 
 
-def ldl(tab: InstructionTable, A: SparseSym, order: Optional[Sequence[int]] = None) -> LDLFactor:
-    """Symbolic LDL' of the symmetric matrix whose LOWER triangle is taken from ``A``."""
+def ldl(tab: InstructionTable, A: SparseSym, order=None) -> LDLFactor:
+    """Symbolic LDL' of the symmetric matrix whose LOWER triangle is taken from ``A``.
+    ``order``: None (default method of ``ordering.py``: symamd), a method name, a callable
+    ``A -> permutation`` or an explicit permutation."""
     n = len(A)
-    if order is None:
-        pat = [set() for _ in range(n)]
-        for i, row in enumerate(A):
-            for j in row:
-                if j != i:
-                    pat[i].add(j)
-                    pat[j].add(i)
-        order = minimum_degree_ordering(pat)
+    if order is None or isinstance(order, str) or callable(order):
+        order = _ordering.order(A, order)
     p = list(order)
+    if sorted(p) != list(range(n)):
+        raise ValueError("ldl: the ordering is not a permutation of 0..n-1")
     inv = [0] * n
     for k, o in enumerate(p):
         inv[o] = k

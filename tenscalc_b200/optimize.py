@@ -147,6 +147,9 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
         profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
     problem = code.compile(defines)
     fac = info["factor"]
-    gen_info = dict(nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
+    from .ordering import DEFAULT as default_ordering
+    gen_info = dict(ordering=(ordering if isinstance(ordering, str) else "custom") if ordering is not None
+                    else default_ordering,
+                    nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
                     n_groups=len(problem.groups), n_slots=problem.n_slots)
     return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)

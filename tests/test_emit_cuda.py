@@ -23,7 +23,7 @@ def test_expression_forms():
     assert e(it.I_max_abs, [], ["a", "b"], "r") == "double r=fabs(a); if (r<fabs(b)) r=fabs(b);"
     assert e(it.I_min0, [], ["a"], "r") == "double r=0.0; if (r>a) r=a;"
     assert "DBL_MAX" in e(it.I_clp, [], ["a", "b"], "r") and "if (b<0)" in e(it.I_clp, [], ["a", "b"], "r")
-    assert e(it.I_Dsqrt, [], ["x"], "r") == "const double r=.5*pow(x,-.5);"
+    assert e(it.I_Dsqrt, [], ["x"], "r") == "const double r=.5*tc_pow_m05(x);"
     assert e(it.I_sign, [], ["x"], "r") == "const double r=(x>=0)?1.0:-1.0;"
 
 

@@ -55,6 +55,7 @@ def test_parity_with_oracle(name, batch, kw, backend):
 
 
 def _solve(gen, args, P, V, batch, **opts):
+    opts = {k: v for k, v in opts.items() if not (k == "driver" and v == "warp")}   # the default driver
     obj = gen(batch, **opts)
     for n, _ in gen.parameters:
         getattr(obj, "setP_" + n)(P[n])
@@ -121,3 +122,62 @@ def test_lane_decoupled_driver_parity(name, batch, kw, driver):
         a, b = outs[k][..., ok], out_o[k][..., ok]
         scale = np.maximum(np.abs(b).max(axis=tuple(range(b.ndim - 1)), keepdims=True), 1e-300)
         assert np.max(np.abs(a - b) / scale) <= 1e-8, k
+
+
+def _compare_with_oracle(gen, name, P, V, mu0, maxIter, batch, exact_iter=True, **opts):
+    st_o, it_o, out_o, _ = _oracle(gen, name).solve_batch(P, V, mu0, maxIter)
+    obj = _solve(gen, None, P, V, batch, **opts)
+    st, it, _ = obj.solve(mu0, maxIter, -1)
+    obj.close()
+    assert np.array_equal(st, st_o), f"status: gpu {np.unique(st)} oracle {np.unique(st_o)}"
+    if exact_iter:
+        assert np.array_equal(it, it_o)
+    else:
+        assert np.abs(it.astype(int) - it_o.astype(int)).max() <= 1
+    return st, it
+
+
+@pytest.mark.parametrize("driver", ["warp", "lanes"])
+def test_forced_exit_codes_match_the_reference_driver(driver):
+    """every exit path of ipmPD_CSsolver.c:308-357,696-705,885-920 is produced on purpose and compared with the
+    reference driver: status 8 with its diagnostic bits (16 gradient, 32 equality, 64 gap, 128 mu, 1024/1536/1792
+    step sizes, 2048 regulariser) through a small maxIter, status 1 (infeasible start), status 2 (negative dual
+    through mu0<0) and status 4 (NaN parameter)"""
+    seen = set()
+    for name, kw, batch in (("sls", {}, 256), ("mpc_dcmotor", {}, 256), ("mpc_quadcopter", {"T_": 20, "useInertia": True}, 128)):
+        gen, args = generated(name, **kw)
+        P, V = problems.synthetic_inputs(name, gen, batch, seed=11)
+        for maxIter in (1, 2, 3, 5, 8):                       # status 8 | diagnostic bits
+            st, _ = _compare_with_oracle(gen, name, P, V, args["mu0"], maxIter, batch, driver=driver)
+            seen.update(int(x) for x in np.unique(st))
+        st, _ = _compare_with_oracle(gen, name, P, V, -args["mu0"], args["maxIter"], batch, driver=driver)   # lambda=mu/F<0
+        seen.update(int(x) for x in np.unique(st))
+    # status 1: start outside the box; status 4: NaN in the data
+    gen, args = generated("sls")
+    batch = 256
+    P, V = problems.synthetic_inputs("sls", gen, batch, seed=12)
+    V["x"][:, ::2] = .2                                      # violates x <= .05 on every second instance
+    P["b"][0, 1::4] = np.nan
+    st, _ = _compare_with_oracle(gen, "sls", P, V, args["mu0"], args["maxIter"], batch, driver=driver)
+    seen.update(int(x) for x in np.unique(st))
+    assert {1, 2, 4} <= seen, seen
+    assert any(s & 8 for s in seen) and any(s & 16 for s in seen) and any(s & 64 for s in seen) and \
+        any(s & 128 for s in seen), seen
+    print("exit codes produced and matched:", sorted(seen))
+
+
+def test_queue_driver_set_then_get_outputs_without_solve():
+    """after a work-queue solve the optimum is back in the batch scratchbook: changing a parameter and calling
+    getOutputs (no new solve) re-evaluates the outputs at the optimum, like the other drivers and the reference"""
+    gen, args = generated("sls")
+    batch = 3000
+    P, V = problems.synthetic_inputs("sls", gen, batch, seed=13)
+    res = []
+    for driver in ("warp", "queue"):
+        obj = _solve(gen, args, P, V, batch, driver=driver)
+        obj.solve(args["mu0"], args["maxIter"], -1)
+        obj.setP_b(P["b"] * 1.5)
+        res.append(obj.getOutputs())
+        obj.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
