@@ -43,6 +43,29 @@ class GeneratedSolver:
         return BatchedSolver(self, batch, device, backend, **module_opts)
 
 
+def solver_defines(nU: int, nG: int, nF: int, *, gradTolerance: float = 1e-4, equalTolerance: float = 1e-4,
+                   desiredDualityGap: float = 1e-5, alphaMin: float = 1e-7, alphaMax: float = 1.0,
+                   coupledAlphas: bool = True, muFactorAggressive: float = .2, muFactorConservative: float = .95,
+                   skipAffine: bool = True, delta: int = 3, scaleInequalities: bool = True, scaleCost: float = 0.0,
+                   scaleEqualities: bool = False, addEye2Hessian: bool = True, adjustAddEye2Hessian: bool = True,
+                   useInertia: bool = False, addEye2HessianUtolerance: float = 1e-6, solverVerboseLevel: int = 1,
+                   **ignored) -> Dict[str, object]:
+    """the #define table cmex2optimizeCS hands to the C driver (lib/cmex2optimizeCS.m:303-331; defaults
+    lib/private/parameters4all.m, parameters4optimize.m)"""
+    return dict(
+        nU=int(nU), nG=int(nG), nF=int(nF),
+        gradTolerance=float(gradTolerance), addEye2HessianUtolerance=float(addEye2HessianUtolerance),
+        equalTolerance=float(equalTolerance), desiredDualityGap=float(desiredDualityGap),
+        scaleCost=int(scaleCost != 0), scaleInequalities=int(bool(scaleInequalities)),
+        scaleEqualities=int(bool(scaleEqualities)),
+        alphaMin=float(alphaMin), alphaMax=float(alphaMax), coupledAlphas=int(bool(coupledAlphas)),
+        setAddEye2Hessian=int(bool(addEye2Hessian)), adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)),
+        useInertia=int(bool(useInertia)), muFactorAggressive=float(muFactorAggressive),
+        muFactorConservative=float(muFactorConservative), delta=int(delta), skipAffine=int(bool(skipAffine)),
+        smallerNewtonMatrix=0, useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0,
+        profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
+
+
 def _name_of(v: Tcalculus) -> str:
     if not v.is_variable():
         raise ValueError("parameters and optimizationVariables must be Tvariables")
@@ -133,18 +156,14 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
         out_info.append((nm, e.shape))
     code.declare_get("getOutputs", srcs, shapes, names)
 
-    defines = dict(
-        nU=len(u), nG=len(G), nF=len(F),
-        gradTolerance=float(gradTolerance), addEye2HessianUtolerance=float(addEye2HessianUtolerance),
-        equalTolerance=float(equalTolerance), desiredDualityGap=float(desiredDualityGap),
-        scaleCost=int(scaleCost != 0), scaleInequalities=int(bool(scaleInequalities)),
-        scaleEqualities=int(bool(scaleEqualities)),
-        alphaMin=float(alphaMin), alphaMax=float(alphaMax), coupledAlphas=int(bool(coupledAlphas)),
-        setAddEye2Hessian=int(bool(addEye2Hessian)), adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)),
-        useInertia=int(bool(useInertia)), muFactorAggressive=float(muFactorAggressive),
-        muFactorConservative=float(muFactorConservative), delta=int(delta), skipAffine=int(skipAffine),
-        smallerNewtonMatrix=0, useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0,
-        profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
+    defines = solver_defines(len(u), len(G), len(F), gradTolerance=gradTolerance, equalTolerance=equalTolerance,
+                             desiredDualityGap=desiredDualityGap, alphaMin=alphaMin, alphaMax=alphaMax,
+                             coupledAlphas=coupledAlphas, muFactorAggressive=muFactorAggressive,
+                             muFactorConservative=muFactorConservative, skipAffine=skipAffine, delta=delta,
+                             scaleInequalities=scaleInequalities, scaleCost=scaleCost, scaleEqualities=scaleEqualities,
+                             addEye2Hessian=addEye2Hessian, adjustAddEye2Hessian=adjustAddEye2Hessian,
+                             useInertia=useInertia, addEye2HessianUtolerance=addEye2HessianUtolerance,
+                             solverVerboseLevel=solverVerboseLevel)
     problem = code.compile(defines)
     fac = info["factor"]
     from .ordering import DEFAULT as default_ordering
