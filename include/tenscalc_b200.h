@@ -84,6 +84,16 @@ int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, con
 int tc_solve_async(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
                    const double *addEye2Hessian, int32_t *status, int32_t *iter);
 
+/* Phased execution of a solve (default for the compiled back end's warp driver; TC_PHASED=0 in the
+ * environment or tc_set_phased(s,0) selects the single-launch solve).  The Newton loop of
+ * ipmPD_CSsolver.c:282-867 is launched in PHASES of a few iterations; between two phases the instances
+ * that are still iterating are compacted into the leading scratchbook columns, so warps stay full although
+ * instances need different numbers of iterations, and at the end every instance is moved back to its own
+ * column.  Per instance the sequence of operations is unchanged (bit-identical results).
+ * tc_set_phases: iteration budget of phase 0,1,... (the last entry repeats); n=0 restores the default. */
+int tc_set_phased(tc_solver *s, int on);
+int tc_set_phases(tc_solver *s, const int32_t *iterations_per_phase, int n);
+
 /* <class>_getOutputs: y[k] is double[batch][tc_output_size(k)], caller-allocated. */
 int tc_get_outputs(tc_solver *s, double *const *y);
 int tc_get_outputs_device(tc_solver *s, double *const *d_y);

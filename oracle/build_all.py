@@ -5,8 +5,12 @@ import sys
 import time
 from concurrent.futures import ProcessPoolExecutor
 
+AFFINE = {"algorithm": "ipmPD_CS", "skipAffine": False}           # Mehrotra predictor (ipmPD_CSsolver.c:576-665, ipmPD_CS.m)
+AFFINE_SMALL = {**AFFINE, "smallerNewtonMatrix": True}            # + reduced Newton matrix (ipmPD_CS.m:242-351)
 CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}),
-           ("mpc_quadcopter", {"T_": 20, "useInertia": True})]   # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
+           ("mpc_quadcopter", {"T_": 20, "useInertia": True}),    # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
+           ("sls", AFFINE), ("mpc_dcmotor", AFFINE), ("mpc_dcmotor", AFFINE_SMALL),
+           ("mpc_quadcopter", {"T_": 20, **AFFINE})]
 
 
 # extra builds of the benchmark workload: the toolbox's default -O0 and -O2 beside the headline -O1

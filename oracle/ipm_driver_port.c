@@ -1,9 +1,8 @@
 /* CPU ORACLE -- test infrastructure only, never linked into or called from the product path.
  *
  * Restatement ("port") of the reference's primal-dual interior-point driver
- * lib/ipmPD_CSsolver.c:132-920 for the option set its C generator can actually emit
- * (lib/cmex2optimizeCS.m:83-93 forces ipmPD_CStimesLambda: skipAffine=1, useLDL=1, large KKT
- * matrix; useInertia 0 or 1).  It is #included at the end of the translation unit written by
+ * lib/ipmPD_CSsolver.c:132-920: skipAffine 0 or 1 (the affine-scaling predictor :576-665),
+ * useInertia 0 or 1, with or without equality/inequality constraints.  It is #included at the end of the translation unit written by
  * oracle/emit_c.py, after the #define table (lib/cmex2optimizeCS.m:303-331) and the generated
  * set/get/copy functions whose names are the reference's `*__` names.
  *
@@ -180,6 +179,50 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
 #endif
         updatePrimalDual__();
 #else
+#if skipAffine == 0
+        {                                                        /* affine-scaling predictor :576-665 */
+            double zero = 0, sigma;
+            getMaxAlphas_a__(&aP, &aDi);
+            aMax = (aP < alphaMax) ? aP : alphaMax;
+            if (aDi < aMax) aMax = aDi;
+            if (aMax >= alphaMin) {
+                aP = aMax;                                       /* try max */
+                setAlphaPrimal__(&aP);
+                getMinF_a__(&ineq);
+                if (ineq < 0) {
+                    aP = alphaMin;                               /* try min */
+                    setAlphaPrimal__(&aP);
+                    getMinF_a__(&ineq);
+                    if (ineq > 0) {
+                        for (aP = aMax * .95; aP >= alphaMin; aP /= 2) {
+                            setAlphaPrimal__(&aP);
+                            getMinF_a__(&ineq);
+                            if (ineq >= 0) break;
+                        }
+                        if (aP < alphaMin) { aP = 0; setAlphaPrimal__(&zero); }
+                    } else { aP = 0; setAlphaPrimal__(&zero); }
+                }
+            } else { aP = 0; setAlphaPrimal__(&zero); }
+            setAlphaDualIneq__(&aP);
+            if (aP > alphaMax / 2
+#if nG > 0
+                && (eq < 100 * equalTolerance || eq < 1e-3)
+#endif
+                ) {                                              /* :627-660 */
+                getRho__(&sigma);
+                if (sigma > 1) sigma = 1;
+                if (sigma < 0) sigma = 0;
+#if delta == 2
+                sigma = sigma * sigma;
+#else
+                sigma = sigma * sigma * sigma;
+#endif
+                mu = sigma * gap / nF;
+                if (mu < muMin) mu = muMin;
+                setMu__(&mu);
+            }
+        }
+#endif
         getMaxAlphas_s__(&aP, &aDi);                             /* :679 */
 #if coupledAlphas != 0
         if (aDi < aP) aP = aDi;                                  /* :681-684 */
@@ -202,6 +245,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
         setAlphaDualIneq__(&aDi);
         updatePrimalDual__();                                    /* :772 */
 
+#if skipAffine != 0
         {                                                        /* barrier update, skipAffine!=0 :782-850 */
             int th_grad = grad < p_max(1e-6, 1e0 * gradTolerance);
             int th_eq = 1;
@@ -223,6 +267,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
                 setMu__(&mu);
             }
         }
+#endif
         if (aP < alphaMin && aDi < alphaMin && aDe < alphaMin) { /* :853-859 */
             mu /= (muFactorConservative * muFactorConservative);
             if (mu < muMin) mu = muMin;

@@ -36,8 +36,8 @@ __global__ void tc_set_kernel(tc_device_image P, int fn, const double *__restric
     if (blockIdx.y == 0 && threadIdx.y == 0) {
         int64_t b = b0 + threadIdx.x;
         if (b < P.batch) {
-            P.group_status[b] &= ~f.children[0];
-            P.group_status[P.stride + b] &= ~f.children[1];
+#pragma unroll
+            for (int w = 0; w < TC_GW; w++) P.group_status[w * P.stride + b] &= ~f.children[w];
         }
     }
 }
@@ -75,6 +75,136 @@ __global__ void tc_sum_iter_kernel(const int32_t *iter, int64_t n, unsigned long
 }
 
 // ------------------------------------------------------------------------------------------
+// phased solve: compaction of the unfinished instances between two phase launches (tc_driver.cuh)
+// ------------------------------------------------------------------------------------------
+// What has to move with an instance: the PERSISTENT scratchbook slots -- every variable (I_set: written by
+// set functions and copies: parameters, primal/dual variables, mu, step sizes, regularisation) and the outputs of
+// the dependency groups that no solver-side set or copy invalidates (parameter-only subexpressions) -- plus
+// the solver loop's locals (P.ps_d/ps_i).  Everything else is recomputed: the moved column's group status is
+// reset to "only the static groups are valid".
+struct tc_compact {
+    const uint32_t *slots;       // persistent slots
+    int32_t n_slots;
+    uint64_t static_mask[TC_GW]; // groups that stay valid when an instance moves
+    double *pool;                // [n_slots][batch]: final state of finished instances whose column was reused
+    uint64_t *pool_status;       // [TC_GW][batch]: their group status (static groups only: evaluation is lazy, a
+                                 // static group that nobody asked for yet is still stale and must stay so)
+    uint8_t *saved;              // [batch]
+    int32_t *holes, *movers;     // [stride] pairing of the current compaction
+    int32_t *n_moves;
+};
+
+__global__ void tc_phase_reset_kernel(tc_device_image P, tc_compact C) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < P.stride) {
+        P.orig[i] = i < P.batch ? (int32_t)i : -1;
+        P.ps_i[(size_t)1 * P.stride + i] = 0;
+    }
+    if (i < P.batch) C.saved[i] = 0;
+    if (i == 0) { *P.n_live = (int32_t)P.batch; *C.n_moves = 0; }
+}
+
+// ONE CTA: ranks the columns [0, n_live) by "still running" and pairs the k-th finished column below the new
+// n_live (a hole) with the k-th running column above it (a mover)
+__global__ void __launch_bounds__(1024) tc_compact_plan_kernel(tc_device_image P, tc_compact C) {
+    __shared__ int part[1024];
+    __shared__ int s_new, s_lnn;
+    const int n_old = *P.n_live, T = blockDim.x, tid = threadIdx.x;
+    const int32_t *flags = P.ps_i + (size_t)1 * P.stride;            // PS_flags
+    const int per = (n_old + T - 1) / T, a = min(tid * per, n_old), b = min(a + per, n_old);
+    int cnt = 0;
+    for (int p = a; p < b; p++) cnt += flags[p] & 1;
+    part[tid] = cnt;
+    __syncthreads();
+    for (int o = 1; o < T; o <<= 1) {                                 // inclusive scan
+        const int v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    if (tid == T - 1) s_new = part[tid];
+    __syncthreads();
+    const int n_new = s_new, L0 = part[tid] - cnt;                    // running columns before `a`
+    int c2 = 0;                                                       // running columns in [a,b) below n_new
+    for (int p = a; p < b && p < n_new; p++) c2 += flags[p] & 1;
+    __syncthreads();
+    part[tid] = c2;
+    __syncthreads();
+    for (int o = T >> 1; o; o >>= 1) {
+        if (tid < o) part[tid] += part[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) s_lnn = part[0];
+    __syncthreads();
+    const int lnn = s_lnn;
+    int L = L0;
+    for (int p = a; p < b; p++) {
+        const int live = flags[p] & 1;
+        if (p < n_new && !live) C.holes[p - L] = p;
+        if (p >= n_new && live) C.movers[L - lnn] = p;
+        L += live;
+    }
+    if (tid == 0) { *C.n_moves = n_new - lnn; *P.n_live = n_new; }
+}
+
+__device__ __forceinline__ void tc_column_to_pool(const tc_device_image &P, const tc_compact &C, int64_t col, int64_t id) {
+    for (int k = threadIdx.x; k < C.n_slots; k += blockDim.x)
+        C.pool[(size_t)k * P.batch + id] = TC_M(P, C.slots[k], col);
+    for (int w = threadIdx.x; w < TC_GW; w += blockDim.x)
+        C.pool_status[(size_t)w * P.batch + id] = P.group_status[(size_t)w * P.stride + col] & C.static_mask[w];
+}
+
+// one CTA per move (grid-stride): park the finished instance that sits in the hole, then move the mover in
+__global__ void __launch_bounds__(256) tc_compact_move_kernel(tc_device_image P, tc_compact C) {
+    const int n = *C.n_moves;
+    for (int m = blockIdx.x; m < n; m += gridDim.x) {
+        const int64_t h = C.holes[m], q = C.movers[m];
+        const int32_t id_h = P.orig[h];
+        if (id_h >= 0) tc_column_to_pool(P, C, h, id_h);
+        __syncthreads();
+        for (int k = threadIdx.x; k < C.n_slots; k += blockDim.x) {
+            const uint32_t sl = C.slots[k];
+            TC_M(P, sl, h) = TC_M(P, sl, q);
+        }
+        for (int k = threadIdx.x; k < TC_PS_ND; k += blockDim.x) P.ps_d[(size_t)k * P.stride + h] = P.ps_d[(size_t)k * P.stride + q];
+        for (int k = threadIdx.x; k < TC_PS_NI; k += blockDim.x) P.ps_i[(size_t)k * P.stride + h] = P.ps_i[(size_t)k * P.stride + q];
+        for (int w = threadIdx.x; w < TC_GW; w += blockDim.x)
+            P.group_status[(size_t)w * P.stride + h] = P.group_status[(size_t)w * P.stride + q] & C.static_mask[w];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (id_h >= 0) C.saved[id_h] = 1;
+            P.orig[h] = P.orig[q];
+            P.orig[q] = -1;
+            P.ps_i[(size_t)1 * P.stride + q] = 0;                     // the vacated column holds nothing that runs
+        }
+        __syncthreads();
+    }
+}
+
+// end of a phased solve: every instance goes back to its home column (getOutputs, and a later set +
+// getOutputs without a new solve, evaluate the output groups there).  Two kernels: park every displaced
+// instance, then restore everything that is parked.
+__global__ void __launch_bounds__(256) tc_restore_park_kernel(tc_device_image P, tc_compact C) {
+    for (int64_t col = blockIdx.x; col < P.stride; col += gridDim.x) {
+        const int32_t id = P.orig[col];
+        if (id >= 0 && id != col) {
+            tc_column_to_pool(P, C, col, id);
+            if (threadIdx.x == 0) C.saved[id] = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) tc_restore_home_kernel(tc_device_image P, tc_compact C) {
+    for (int64_t id = blockIdx.x; id < P.batch; id += gridDim.x) {
+        if (!C.saved[id]) continue;
+        for (int k = threadIdx.x; k < C.n_slots; k += blockDim.x)
+            TC_M(P, C.slots[k], id) = C.pool[(size_t)k * P.batch + id];
+        for (int w = threadIdx.x; w < TC_GW; w += blockDim.x)
+            P.group_status[(size_t)w * P.stride + id] = C.pool_status[(size_t)w * P.batch + id];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct tc_solver {
@@ -94,11 +224,16 @@ struct tc_solver {
     float last_ms = 0.f;
     // compiled back end: per-problem module (tenscalc_b200/emit_cuda.py), NULL = tape interpreter
     void *module = nullptr;
-    int (*mod_solve)(const tc_device_image *, double, int, double, double, int32_t *, int32_t *, void *) = nullptr;
+    int (*mod_solve)(const tc_device_image *, double, int, double, double, int32_t *, int32_t *, void *, int, int) = nullptr;
+    // phased solve (tc_driver.cuh): compaction state and the iteration budget of every phase
+    tc_compact cmp{};
+    int phased = 0, mod_phased = 1;
+    std::vector<int> phase_len;          // explicit schedule (tc_set_phases); empty: the default schedule
+    int32_t *last_iter = nullptr;        // d_iter of the last solve (tc_total_newton_steps)
     int (*mod_eval)(const tc_device_image *, int, void *) = nullptr;
 };
 
-#define TCM_ABI 1
+#define TCM_ABI 2
 
 #define TC_CUDA(x)                           \
     do {                                     \
@@ -149,8 +284,17 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     s->batch = batch;
     s->stride = (batch + 255) / 256 * 256;   // whole CTAs for every back end (TC_BLOCK, 32*TC_LOCKSTEP <= 256)
     const int64_t n_slots = ih[1], n_groups = ih[2], n_funcs = ih[3], n_sets = ih[4], n_out = ih[5],
-                  tape_cells = ih[6], n_consts = ih[7], io_words = ih[8];
+                  tape_cells = ih[6], n_consts = ih[7], io_words = ih[8], n_persist = ih[11];
     s->n_slots = n_slots;
+    // a truncated or foreign image must fail with TC_EFORMAT, not with out-of-bounds reads
+    if (n_slots <= 0 || n_groups < 0 || n_groups > TC_MAXGROUPS || n_funcs < FN_USER0 + n_sets || n_sets < 0 || n_out < 0 ||
+        tape_cells < 0 || n_consts < 0 || io_words < 0 || n_persist < 0 || n_persist > n_slots || ih[9] != TC_RING ||
+        ih[10] != TC_BUNDLE || tape_cells % TC_BUNDLE || ih[12] != TC_GW ||
+        (uint64_t)n_funcs > image_bytes / sizeof(tc_func) || (uint64_t)tape_cells > image_bytes / sizeof(uint4) ||
+        (uint64_t)io_words > image_bytes / 4 || (uint64_t)n_consts > image_bytes / 8) {
+        delete s;
+        return TC_EFORMAT;
+    }
     auto pad16 = [](size_t b) { return (b + 15) / 16 * 16; };
     const char *p = (const char *)(dh + 16);
     const uint32_t *group_start = (const uint32_t *)p; p += pad16((n_groups + 1) * 4);
@@ -160,8 +304,17 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     const uint32_t *io = (const uint32_t *)p;          p += pad16(io_words * 4);
     const uint32_t *set_fids = (const uint32_t *)p;    p += pad16(n_sets * 4);
     const uint32_t *out_sizes = (const uint32_t *)p;   p += pad16(n_out * 4);
-    if ((size_t)(p - (const char *)image) > image_bytes || n_groups > 128 || ih[9] != TC_RING ||
-        ih[10] != TC_BUNDLE || tape_cells % TC_BUNDLE || n_consts > TC_MAXCONST) {
+    const uint32_t *persist = (const uint32_t *)p;     p += pad16(n_persist * 4);
+    bool ok = (size_t)(p - (const char *)image) <= image_bytes;
+    for (int64_t g = 0; ok && g < n_groups; g++) ok = group_start[g] <= group_start[g + 1] && group_start[g + 1] <= tape_cells;
+    for (int64_t f = 0; ok && f < n_funcs; f++)
+        ok = (uint64_t)funcs[f].io_off + funcs[f].io_cnt <= (uint64_t)io_words;
+    uint64_t out_total = 0;
+    for (int64_t k = 0; ok && k < n_out; k++) out_total += out_sizes[k];
+    for (int64_t k = 0; ok && k < n_sets; k++) ok = set_fids[k] >= FN_USER0 && set_fids[k] < n_funcs;
+    for (int64_t k = 0; ok && k < n_persist; k++) ok = persist[k] < n_slots;
+    if (ok) ok = out_total == funcs[FN_getOutputs].io_cnt;
+    if (!ok) {
         delete s;
         return TC_EFORMAT;
     }
@@ -184,19 +337,46 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     s->allocs.push_back(d);
     I.m = (double *)d;
     TC_TRY((int)cudaMemsetAsync(d, 0, mbytes, s->stream));
-    TC_TRY((int)cudaMalloc(&d, 2 * s->stride * sizeof(uint64_t)));
+    TC_TRY((int)cudaMalloc(&d, TC_GW * s->stride * sizeof(uint64_t)));
     s->allocs.push_back(d);
     I.group_status = (uint64_t *)d;
-    TC_TRY((int)cudaMemsetAsync(d, 0, 2 * s->stride * sizeof(uint64_t), s->stream));
-    TC_TRY((int)cudaMalloc(&d, 256 * sizeof(unsigned long long)));   // [0,128): instance-, [128,256): warp-executions
+    TC_TRY((int)cudaMemsetAsync(d, 0, TC_GW * s->stride * sizeof(uint64_t), s->stream));
+    TC_TRY((int)cudaMalloc(&d, 2 * TC_MAXGROUPS * sizeof(unsigned long long)));   // instance-, then warp-executions
     s->allocs.push_back(d);
     I.group_count = (unsigned long long *)d;
-    TC_TRY((int)cudaMemsetAsync(d, 0, 256 * sizeof(unsigned long long), s->stream));
+    TC_TRY((int)cudaMemsetAsync(d, 0, 2 * TC_MAXGROUPS * sizeof(unsigned long long), s->stream));
     TC_TRY((int)cudaMalloc(&d, s->stride * sizeof(int32_t) * 2 + 16));
     s->allocs.push_back(d);
+    TC_TRY((int)cudaMemsetAsync(d, 0, s->stride * sizeof(int32_t) * 2 + 16, s->stream));
     s->d_status = (int32_t *)d;
     s->d_iter = s->d_status + s->stride;
     s->d_sum = (unsigned long long *)(s->d_iter + s->stride);
+    s->last_iter = s->d_iter;
+    // phased solve: parked solver locals, column -> instance map, compaction work space, parking pool
+    {
+        const char *e = getenv("TC_PHASED");
+        s->phased = (e && e[0] == '0') ? 0 : 1;
+        const size_t st = (size_t)s->stride;
+        TC_TRY((int)cudaMalloc(&d, TC_PS_ND * st * sizeof(double)));
+        s->allocs.push_back(d);
+        I.ps_d = (double *)d;
+        TC_TRY((int)cudaMalloc(&d, (TC_PS_NI + 3) * st * sizeof(int32_t) + 64));
+        s->allocs.push_back(d);
+        TC_TRY((int)cudaMemsetAsync(d, 0, (TC_PS_NI + 3) * st * sizeof(int32_t) + 64, s->stream));
+        I.ps_i = (int32_t *)d;
+        I.orig = I.ps_i + TC_PS_NI * st;
+        s->cmp.holes = I.orig + st;
+        s->cmp.movers = s->cmp.holes + st;
+        I.n_live = s->cmp.movers + st;
+        s->cmp.n_moves = I.n_live + 1;
+        TC_TRY(tc_upload(s, persist, n_persist * 4, 0, (const void **)&s->cmp.slots));
+        s->cmp.n_slots = (int32_t)n_persist;
+        for (int w = 0; w < TC_GW; w++) s->cmp.static_mask[w] = (uint64_t)ih[32 + w];
+        TC_TRY((int)cudaMalloc(&d, (size_t)batch + 16));
+        s->allocs.push_back(d);
+        s->cmp.saved = (uint8_t *)d;
+        s->cmp.pool = nullptr;           // allocated by the first phased solve (n_persist x batch doubles)
+    }
     I.stride = s->stride;
     I.n_slots = n_slots;
     I.batch = batch;
@@ -206,6 +386,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     I.m_work = nullptr;
     I.queue = nullptr;
     I.work_tiles = 0;
+    I.phased = 0;
     tc_defines &D = I.def;
     D.nU = (int32_t)ih[16]; D.nG = (int32_t)ih[17]; D.nF = (int32_t)ih[18];
     D.scaleCost = (int32_t)ih[19]; D.scaleInequalities = (int32_t)ih[20]; D.coupledAlphas = (int32_t)ih[21];
@@ -214,7 +395,10 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     D.gradTolerance = dh[0]; D.addEye2HessianUtolerance = dh[1]; D.equalTolerance = dh[2];
     D.desiredDualityGap = dh[3]; D.alphaMin = dh[4]; D.alphaMax = dh[5];
     D.muFactorAggressive = dh[6]; D.muFactorConservative = dh[7];
-    if (!D.skipAffine) { tc_destroy(s); return TC_EFORMAT; }   // Mehrotra path: not emitted by cmex2optimizeCS
+    if (!D.skipAffine && D.nF > 0 && (n_funcs <= FN_getRho || !funcs[FN_getRho].io_cnt || !funcs[FN_getMinF_a].io_cnt)) {
+        tc_destroy(s);                 // skipAffine=0 needs getMaxAlphas_a__/getMinF_a__/getRho__ (ipmPD_CS.m:313-315)
+        return TC_EFORMAT;
+    }
     s->funcs.assign(funcs, funcs + n_funcs);
     s->set_fids.assign(set_fids, set_fids + n_sets);
     s->out_sizes.assign(out_sizes, out_sizes + n_out);
@@ -245,7 +429,8 @@ int tc_destroy(tc_solver *s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
-    if (s->module) dlclose(s->module);
+    // the per-problem module stays mapped until the process exits (its kernels are what ran: keep it visible to
+    // tools that list the loaded native code after the handles are gone)
     delete s;
     return 0;
 }
@@ -265,6 +450,7 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     auto eval = (decltype(s->mod_eval))dlsym(h, "tcm_eval");
     auto load = (int (*)(void))dlsym(h, "tcm_load");
     auto work = (int (*)(void))dlsym(h, "tcm_work_tiles");   // > 0: work-queue driver, resident warps
+    auto phs = (int (*)(void))dlsym(h, "tcm_phased");        // 1: the module's driver can run a solve in phases
     if (!load || !abi || !img || !blk || !fp || !solve || !eval || abi() != TCM_ABI || img() != (int)sizeof(tc_device_image) ||
         blk() <= 0 || s->stride % blk() || (fingerprint && strcmp(fingerprint, fp()))) {
         dlclose(h);
@@ -299,6 +485,8 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     s->module = h;
     s->mod_solve = solve;
     s->mod_eval = eval;
+    s->mod_phased = phs ? phs() : 0;
+    fprintf(stderr, "tenscalc_b200: module %s attached (%s)\n", path, s->mod_phased && s->phased ? "phased solve" : "single-launch solve");
     // Warm-up launch over an EMPTY batch (one CTA, every lane invalid: nothing is read or written but
     // the lanes' own group-status words): the first launch of a module makes the driver size the
     // local-memory pool for the kernel's stack frames, 0.1-0.3 s that would otherwise be charged to the
@@ -307,7 +495,7 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     w.batch = 0;
     w.stride = blk();
     if (w.queue) rc = (int)cudaMemsetAsync(w.queue, 0, sizeof(unsigned long long), s->stream);
-    if (!rc) rc = solve(&w, 1.0, 1, 0.0, 0.0, s->d_status, s->d_iter, (void *)s->stream);
+    if (!rc) rc = solve(&w, 1.0, 1, 0.0, 0.0, s->d_status, s->d_iter, (void *)s->stream, 1, 0);
     if (!rc) rc = (int)cudaStreamSynchronize(s->stream);
     return rc;
 }
@@ -335,6 +523,7 @@ int tc_set_device(tc_solver *s, int i, const double *d_values, int64_t batch_str
     TC_CUDA(cudaSetDevice(s->device));
     const uint32_t fn = s->set_fids[i];
     const uint32_t n = s->funcs[fn].io_cnt;
+    if (n == 0) return 0;
     dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
     tc_set_kernel<<<grid, block, 0, s->stream>>>(s->img, (int)fn, d_values, batch_stride);
     s->launches++;
@@ -351,22 +540,89 @@ int tc_set(tc_solver *s, int i, const double *values, int64_t batch_stride) {
     return tc_set_device(s, i, s->d_stage, batch_stride);
 }
 
+// iteration budget of phase k of a phased solve.  Default: one iteration (instances that start infeasible
+// leave at once), then short phases while most instances finish, longer ones for the stragglers.
+static int tc_phase_len(const tc_solver *s, int k, int covered) {
+    if (!s->phase_len.empty()) return s->phase_len[k < (int)s->phase_len.size() ? k : (int)s->phase_len.size() - 1];
+    if (covered == 0) return 1;
+    if (covered < 64) return 2;
+    if (covered < 128) return 4;
+    if (covered < 256) return 8;
+    if (covered < 512) return 16;
+    return 32;
+}
+
+int tc_set_phases(tc_solver *s, const int32_t *lens, int n) {
+    if (!s || n < 0 || (n > 0 && !lens)) return TC_EINVAL;
+    for (int k = 0; k < n; k++)
+        if (lens[k] <= 0) return TC_EINVAL;
+    s->phase_len.assign(lens, lens + n);
+    s->phased = n > 0 || s->phased;
+    return 0;
+}
+
+int tc_set_phased(tc_solver *s, int on) {
+    if (!s) return TC_EINVAL;
+    s->phased = on != 0;
+    return 0;
+}
+
 int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
                     const double *addEye2Hessian, int32_t *d_status, int32_t *d_iter) {
     if (!s || !mu0 || !maxIter || !addEye2Hessian || !d_status || !d_iter) return TC_EINVAL;
-    (void)saveIter;   // allowSave is a code-generation-time option of the reference (cmex2optimizeCS.m:326)
+    // saveIter: the reference dumps the KKT matrix values at that iteration when the solver was GENERATED with
+    // allowSave (cmex2optimizeCS.m:326, ipmPD_CSsolver.c:562-564,672-674); the generators here always emit
+    // allowSave=0, for which the reference ignores the argument too
+    (void)saveIter;
+    if (!s->module && s->img.n_consts > TC_MAXCONST) return TC_EFORMAT;   // interpreter: constant pool lives in shared memory
     TC_CUDA(cudaSetDevice(s->device));
     TC_CUDA(cudaEventRecord(s->ev0, s->stream));
-    if (s->module) {
-        if (s->img.queue) TC_CUDA(cudaMemsetAsync(s->img.queue, 0, sizeof(unsigned long long), s->stream));
-        TC_CUDA((cudaError_t)s->mod_solve(&s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status,
-                                          d_iter, (void *)s->stream));
-    } else {
+    s->last_iter = d_iter;
+    const bool phased = s->phased && (!s->module || s->mod_phased) && !s->img.queue && s->cmp.n_slots > 0;
+    auto launch = [&](int first, int iters) -> int {
+        if (s->module)
+            return s->mod_solve(&s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter,
+                                (void *)s->stream, first, iters);
         tc_solve_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(
-            s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter);
+            s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter, first, iters);
+        return (int)cudaGetLastError();
+    };
+    if (!phased) {
+        s->img.phased = 0;
+        if (s->img.queue) TC_CUDA(cudaMemsetAsync(s->img.queue, 0, sizeof(unsigned long long), s->stream));
+        TC_CUDA((cudaError_t)launch(1, 0));
+        s->launches++;
+    } else {
+        if (!s->cmp.pool) {
+            void *d = nullptr;
+            TC_CUDA(cudaMalloc(&d, ((size_t)s->cmp.n_slots + TC_GW) * (size_t)s->batch * sizeof(double)));
+            s->allocs.push_back(d);
+            s->cmp.pool = (double *)d;
+            s->cmp.pool_status = (uint64_t *)(s->cmp.pool + (size_t)s->cmp.n_slots * (size_t)s->batch);
+        }
+        s->img.phased = 1;
+        const unsigned nb = (unsigned)((s->stride + 255) / 256);
+        tc_phase_reset_kernel<<<nb, 256, 0, s->stream>>>(s->img, s->cmp);
+        s->launches++;
+        // the loop body runs maxIter+1 times for an instance that hits the iteration limit (:284,308-313)
+        const int64_t total = (int64_t)(*maxIter > 0 ? *maxIter : 0) + 1;
+        int64_t covered = 0;
+        for (int k = 0; covered < total; k++) {
+            const int len = tc_phase_len(s, k, (int)covered);
+            TC_CUDA((cudaError_t)launch(k == 0, len));
+            covered += len;
+            if (covered < total) {
+                tc_compact_plan_kernel<<<1, 1024, 0, s->stream>>>(s->img, s->cmp);
+                tc_compact_move_kernel<<<1184, 256, 0, s->stream>>>(s->img, s->cmp);
+                s->launches += 2;
+            }
+            s->launches++;
+        }
+        tc_restore_park_kernel<<<1184, 256, 0, s->stream>>>(s->img, s->cmp);
+        tc_restore_home_kernel<<<1184, 256, 0, s->stream>>>(s->img, s->cmp);
+        s->launches += 2;
         TC_CUDA(cudaGetLastError());
     }
-    s->launches++;
     TC_CUDA(cudaEventRecord(s->ev1, s->stream));
     return 0;
 }
@@ -407,6 +663,7 @@ int tc_get_outputs_device(tc_solver *s, double *const *d_y) {
     TC_CUDA((cudaError_t)tc_launch_eval(s, (int)FN_getOutputs));
     for (size_t k = 0; k < s->out_sizes.size(); k++) {
         const uint32_t n = s->out_sizes[k];
+        if (n == 0) continue;
         dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
         tc_gather_kernel<<<grid, block, 0, s->stream>>>(s->img, s->out_offs[k], n, d_y[k]);
         s->launches++;
@@ -420,6 +677,7 @@ int tc_get_outputs(tc_solver *s, double *const *y) {
     TC_CUDA((cudaError_t)tc_launch_eval(s, (int)FN_getOutputs));
     for (size_t k = 0; k < s->out_sizes.size(); k++) {
         const uint32_t n = s->out_sizes[k];
+        if (n == 0) continue;
         dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
         tc_gather_kernel<<<grid, block, 0, s->stream>>>(s->img, s->out_offs[k], n, s->d_stage);
         s->launches++;
@@ -455,9 +713,9 @@ int tc_num_groups(const tc_solver *s) { return s ? (int)s->img.n_groups : TC_EIN
 static int tc_counts(tc_solver *s, int64_t *counts, int reset, int which) {
     if (!s || !counts) return TC_EINVAL;
     TC_CUDA(cudaSetDevice(s->device));
-    unsigned long long h[128];
-    TC_CUDA(cudaMemcpyAsync(h, s->img.group_count + 128 * which, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
-    if (reset) TC_CUDA(cudaMemsetAsync(s->img.group_count + 128 * which, 0, sizeof(h), s->stream));
+    unsigned long long h[TC_MAXGROUPS];
+    TC_CUDA(cudaMemcpyAsync(h, s->img.group_count + TC_MAXGROUPS * which, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    if (reset) TC_CUDA(cudaMemsetAsync(s->img.group_count + TC_MAXGROUPS * which, 0, sizeof(h), s->stream));
     TC_CUDA(cudaStreamSynchronize(s->stream));
     for (int g = 0; g < s->img.n_groups; g++) counts[g] = (int64_t)h[g];
     return 0;
@@ -470,7 +728,7 @@ int tc_total_newton_steps(tc_solver *s, int64_t *steps) {
     if (!s || !steps) return TC_EINVAL;
     TC_CUDA(cudaSetDevice(s->device));
     TC_CUDA(cudaMemsetAsync(s->d_sum, 0, sizeof(unsigned long long), s->stream));
-    tc_sum_iter_kernel<<<148, 256, 0, s->stream>>>(s->d_iter, s->batch, s->d_sum);
+    tc_sum_iter_kernel<<<148, 256, 0, s->stream>>>(s->last_iter, s->batch, s->d_sum);   // iter[] of the last solve, wherever it went
     s->launches++;
     unsigned long long h = 0;
     TC_CUDA(cudaMemcpyAsync(&h, s->d_sum, sizeof(h), cudaMemcpyDeviceToHost, s->stream));

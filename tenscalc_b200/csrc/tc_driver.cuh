@@ -31,6 +31,21 @@
 
 // line-search automaton, one state per `getMinF_s__` evaluation of ipmPD_CSsolver.c:690-756
 enum { LS_DONE = 0, LS_TRYMAX, LS_RECHECK, LS_TRYMIN, LS_SCAN, LS_SCAN_RECHECK };
+// affine-step automaton, one state per `getMinF_a__` evaluation of ipmPD_CSsolver.c:580-625
+enum { AF_DONE = 0, AF_TRYMAX, AF_TRYMIN, AF_SCAN };
+
+// PHASED EXECUTION.  One solve = a sequence of launches of this loop ("phases", tc_abi.cu): a phase runs at
+// most `phase_iters` Newton iterations per instance and parks the loop's locals of the unfinished
+// instances in P.ps_d / P.ps_i; between phases the host-enqueued compaction kernel moves the unfinished
+// instances into the leading scratchbook columns, so every warp of the next phase is full again (a
+// statically assigned warp runs until its slowest lane is done: 34.9 iterations per warp against 27.3 per
+// instance on mpc_quadcopter) and the few instances that need hundreds of iterations end up together in
+// one warp.  The per-instance sequence of operations -- hence every rounding -- is unchanged.
+// phase_iters == 0: the whole solve in this launch (tape interpreter, lanes/queue drivers).
+enum { PS_aeU = 0, PS_aeEq, PS_mu, PS_muMin, PS_gapTol, PS_alphaMax, PS_alphaPrimal, PS_alphaDualEq, PS_alphaDualIneq,
+       PS_mp, PS_mn };                                     // TC_PS_ND doubles per column
+enum { PS_iter = 0, PS_flags };                            // TC_PS_NI ints; flags: 1 running, 2 updU, 4 updEq
+static_assert(PS_mn + 1 == TC_PS_ND && PS_flags + 1 == TC_PS_NI, "phase-state layout");
 
 typedef double tc_dT[TC_TILES];
 typedef bool tc_bT[TC_TILES];
@@ -43,9 +58,12 @@ __device__ __forceinline__ bool tc_any_tile(const tc_bT &x) {
     return TC_ANY(a);
 }
 
+// valid: the lane's column holds an instance this launch works on; pos: the column; done_out: the
+// instance finished in this launch (status_out/iter_out are final)
 __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &P, const tc_bT &valid, double mu0,
                                              int maxIter, double aeU0, double aeEq0, tc_iT &status_out,
-                                             tc_iT &iter_out) {
+                                             tc_iT &iter_out, tc_bT &done_out, const int64_t (&pos)[TC_TILES],
+                                             int phase_first, int phase_iters) {
     const tc_defines &D = P.def;
     const bool hasF = D.nF > 0, hasG = D.nG > 0;
     const bool adjust = D.setAddEye2Hessian && D.adjustAddEye2Hessian;
@@ -61,6 +79,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         norminf_grad[t] = norminf_eq[t] = gap[t] = ineq[t] = ineq1[t] = dual[t] = mp[t] = mn[t] = 0;
     }
 
+    if (phase_first) {
     if (D.setAddEye2Hessian) {                                              // :150-155
         tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, run);
         tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, run);
@@ -79,8 +98,24 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         tc_copy(c, P, FN_initDualIneq, run);
     }
     if (hasG) tc_copy(c, P, FN_initDualEqX, run);                           // :232-235
+    } else {                                                                // resume: the locals parked by the last phase
+        TC_FORT if (valid[t]) {
+            const double *d = P.ps_d + pos[t];
+            const int32_t *q = P.ps_i + pos[t];
+            const int64_t S = P.stride;
+            aeU[t] = d[PS_aeU * S]; aeEq[t] = d[PS_aeEq * S]; mu[t] = d[PS_mu * S]; muMin[t] = d[PS_muMin * S];
+            gapTol[t] = d[PS_gapTol * S]; alphaMax_[t] = d[PS_alphaMax * S]; alphaPrimal[t] = d[PS_alphaPrimal * S];
+            alphaDualEq[t] = d[PS_alphaDualEq * S]; alphaDualIneq[t] = d[PS_alphaDualIneq * S];
+            mp[t] = d[PS_mp * S]; mn[t] = d[PS_mn * S];
+            iter[t] = q[PS_iter * S];
+            const int fl = q[PS_flags * S];
+            run[t] = (fl & 1) != 0; updU[t] = (fl & 2) != 0; updEq[t] = (fl & 4) != 0;
+        }
+    }
+    tc_bT entered;
+    TC_FORT entered[t] = run[t];
 
-    while (tc_any_tile(run)) {                                              // :282
+    for (int phase_it = 0; tc_any_tile(run) && (phase_iters == 0 || phase_it < phase_iters); phase_it++) {   // :282
         TC_FORT {
             if (run[t]) iter[t]++;
             if (run[t] && iter[t] > maxIter) { status[t] = 8; run[t] = false; }   // :308-313
@@ -185,6 +220,73 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             continue;
         }
 
+        // ---- affine-scaling (Mehrotra) predictor, skipAffine==0 (:576-665) ----
+        if (!D.skipAffine) {
+            tc_get(c, P, FN_getMaxAlphas_a, run);
+            tc_value(c, P, FN_getMaxAlphas_a, 0, run, v0);
+            tc_value(c, P, FN_getMaxAlphas_a, 1, run, v1);
+            tc_iT af;
+            tc_bT azero, aev;
+            TC_FORT {
+                af[t] = AF_DONE;
+                azero[t] = false;
+                if (run[t]) {
+                    alphaPrimal[t] = v0[t];
+                    alphaDualIneq[t] = v1[t];
+                    alphaMax_[t] = (alphaPrimal[t] < D.alphaMax) ? alphaPrimal[t] : D.alphaMax;
+                    if (alphaDualIneq[t] < alphaMax_[t]) alphaMax_[t] = alphaDualIneq[t];
+                    if (alphaMax_[t] >= D.alphaMin) { alphaPrimal[t] = alphaMax_[t]; af[t] = AF_TRYMAX; }   // try max
+                    else { alphaPrimal[t] = 0; azero[t] = true; }
+                }
+            }
+            while (true) {
+                TC_FORT pr[t] = azero[t] || af[t] != AF_DONE;
+                tc_set_scalar(c, P, FN_setAlphaPrimal, alphaPrimal, pr);
+                TC_FORT { azero[t] = false; aev[t] = af[t] != AF_DONE; }
+                if (!tc_any_tile(aev)) break;
+                tc_get(c, P, FN_getMinF_a, aev);
+                tc_value(c, P, FN_getMinF_a, 0, aev, v0);
+                TC_FORT {
+                    const double f = v0[t];
+                    if (aev[t]) switch (af[t]) {
+                    case AF_TRYMAX:
+                        if (f < 0) { alphaPrimal[t] = D.alphaMin; af[t] = AF_TRYMIN; }               // try min
+                        else af[t] = AF_DONE;
+                        break;
+                    case AF_TRYMIN:
+                        if (f > 0) {                                                              // between min and max
+                            alphaPrimal[t] = alphaMax_[t] * .95;
+                            if (alphaPrimal[t] >= D.alphaMin) af[t] = AF_SCAN;
+                            else { alphaPrimal[t] = 0; azero[t] = true; af[t] = AF_DONE; }
+                        } else { alphaPrimal[t] = 0; azero[t] = true; af[t] = AF_DONE; }
+                        break;
+                    case AF_SCAN:
+                        if (f >= 0) af[t] = AF_DONE;
+                        else {
+                            alphaPrimal[t] /= 2;
+                            if (!(alphaPrimal[t] >= D.alphaMin)) { alphaPrimal[t] = 0; azero[t] = true; af[t] = AF_DONE; }
+                        }
+                        break;
+                    }
+                }
+            }
+            tc_set_scalar(c, P, FN_setAlphaDualIneq, alphaPrimal, run);
+            // mu from the predicted complementarity (sigma = rho^delta), only after a long affine step (:627-660)
+            TC_FORT pr[t] = run[t] && alphaPrimal[t] > D.alphaMax / 2 &&
+                            (!hasG || norminf_eq[t] < 100 * D.equalTolerance || norminf_eq[t] < 1e-3);
+            tc_get(c, P, FN_getRho, pr);
+            tc_value(c, P, FN_getRho, 0, pr, v0);
+            TC_FORT if (pr[t]) {
+                double sigma = v0[t];
+                if (sigma > 1) sigma = 1;
+                if (sigma < 0) sigma = 0;
+                sigma = (D.delta == 2) ? sigma * sigma : sigma * sigma * sigma;
+                mu[t] = sigma * gap[t] / D.nF;
+                if (mu[t] < muMin[t]) mu[t] = muMin[t];
+            }
+            tc_set_scalar(c, P, FN_setMu, mu, pr);
+        }
+
         // ---- combined search direction (:679-772) ----
         tc_get(c, P, FN_getMaxAlphas_s, run);
         tc_value(c, P, FN_getMaxAlphas_s, 0, run, v0);
@@ -277,7 +379,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         // ---- barrier parameter update, skipAffine!=0 (:782-859) ----
         TC_FORT {
             bool set_mu = false, reinit_dual = false;
-            if (run[t]) {
+            if (run[t] && D.skipAffine) {
                 const bool th_grad = norminf_grad[t] < TC_MAX(1e-6, 1e0 * D.gradTolerance);
                 const bool th_eq = !hasG || norminf_eq[t] < TC_MAX(1e-5, 1e0 * D.equalTolerance);
                 if (alphaPrimal[t] > alphaMax_[t] / 2 && th_grad && th_eq) {
@@ -314,7 +416,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
 
     // ---- diagnostic bits when maxIter was reached (:885-920) ----
     tc_bT diag;
-    TC_FORT diag[t] = valid[t] && status[t] == 8;
+    TC_FORT diag[t] = entered[t] && !run[t] && status[t] == 8;
     if (tc_any_tile(diag)) {
         tc_get(c, P, FN_getNorminf_Grad, diag);
         tc_value(c, P, FN_getNorminf_Grad, 0, diag, v0);
@@ -343,5 +445,19 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     TC_FORT {
         status_out[t] = status[t];
         iter_out[t] = iter[t];
+        done_out[t] = entered[t] && !run[t];
+    }
+    if (phase_iters != 0) {            // park the locals of the instances that go on in the next phase
+        TC_FORT if (entered[t]) {
+            double *d = P.ps_d + pos[t];
+            int32_t *q = P.ps_i + pos[t];
+            const int64_t S = P.stride;
+            d[PS_aeU * S] = aeU[t]; d[PS_aeEq * S] = aeEq[t]; d[PS_mu * S] = mu[t]; d[PS_muMin * S] = muMin[t];
+            d[PS_gapTol * S] = gapTol[t]; d[PS_alphaMax * S] = alphaMax_[t]; d[PS_alphaPrimal * S] = alphaPrimal[t];
+            d[PS_alphaDualEq * S] = alphaDualEq[t]; d[PS_alphaDualIneq * S] = alphaDualIneq[t];
+            d[PS_mp * S] = mp[t]; d[PS_mn * S] = mn[t];
+            q[PS_iter * S] = iter[t];
+            q[PS_flags * S] = (run[t] ? 1 : 0) | (updU[t] ? 2 : 0) | (updEq[t] ? 4 : 0);
+        }
     }
 }

@@ -63,8 +63,8 @@ __device__ __forceinline__ double tc_lane_value(const tc_lane &c, const tc_devic
 __device__ __forceinline__ void tc_lane_set(tc_lane &c, const tc_device_image &P, int fn, double value) {
     const tc_func *f = P.funcs + fn;
     c.mb[0][(size_t)__ldg(P.io + f->io_off) * TC_TILE] = value;
-    c.st[0][0] &= ~f->children[0];
-    c.st[0][1] &= ~f->children[1];
+#pragma unroll
+    for (int w = 0; w < TC_GW; w++) c.st[0][w] &= ~f->children[w];
 }
 
 // Runs the instance's solver loop until its next get/copy (s.want_*), or to the end (s.pc = -1).
@@ -174,6 +174,57 @@ __device__ __noinline__ void tc_lane_resume(tc_lane_state &s, tc_lane &c, const 
                 continue;
             }
 
+            // ---- affine-scaling (Mehrotra) predictor, skipAffine==0 (:576-665) ----
+            if (!D.skipAffine) {
+                TC_GET(FN_getMaxAlphas_a);
+                s.alphaPrimal = TC_VAL(FN_getMaxAlphas_a, 0);
+                s.alphaDualIneq = TC_VAL(FN_getMaxAlphas_a, 1);
+                s.alphaMax_ = (s.alphaPrimal < D.alphaMax) ? s.alphaPrimal : D.alphaMax;
+                if (s.alphaDualIneq < s.alphaMax_) s.alphaMax_ = s.alphaDualIneq;
+                if (s.alphaMax_ >= D.alphaMin) {
+                    s.alphaPrimal = s.alphaMax_;                            // try max
+                    TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
+                    TC_GET(FN_getMinF_a);
+                    s.ineq = TC_VAL(FN_getMinF_a, 0);
+                    if (s.ineq < 0) {
+                        s.alphaPrimal = D.alphaMin;                         // try min
+                        TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
+                        TC_GET(FN_getMinF_a);
+                        s.ineq = TC_VAL(FN_getMinF_a, 0);
+                        if (s.ineq > 0) {
+                            for (s.alphaPrimal = s.alphaMax_ * .95; s.alphaPrimal >= D.alphaMin; s.alphaPrimal /= 2) {
+                                TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
+                                TC_GET(FN_getMinF_a);
+                                s.ineq = TC_VAL(FN_getMinF_a, 0);
+                                if (s.ineq >= 0) break;
+                            }
+                            if (s.alphaPrimal < D.alphaMin) {
+                                s.alphaPrimal = 0;
+                                TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
+                            }
+                        } else {
+                            s.alphaPrimal = 0;
+                            TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
+                        }
+                    }
+                } else {
+                    s.alphaPrimal = 0;
+                    TC_SET(FN_setAlphaPrimal, s.alphaPrimal);
+                }
+                TC_SET(FN_setAlphaDualIneq, s.alphaPrimal);
+                if (s.alphaPrimal > D.alphaMax / 2 &&
+                    (!hasG || s.norminf_eq < 100 * D.equalTolerance || s.norminf_eq < 1e-3)) {      // :627-660
+                    TC_GET(FN_getRho);
+                    s.curvature = TC_VAL(FN_getRho, 0);                     // sigma (state only: reuses a dead local)
+                    if (s.curvature > 1) s.curvature = 1;
+                    if (s.curvature < 0) s.curvature = 0;
+                    s.curvature = (D.delta == 2) ? s.curvature * s.curvature : s.curvature * s.curvature * s.curvature;
+                    s.mu = s.curvature * s.gap / D.nF;
+                    if (s.mu < s.muMin) s.mu = s.muMin;
+                    TC_SET(FN_setMu, s.mu);
+                }
+            }
+
             // ---- combined search direction and line search (:679-756) ----
             TC_GET(FN_getMaxAlphas_s);
             s.alphaPrimal = TC_VAL(FN_getMaxAlphas_s, 0);
@@ -245,7 +296,8 @@ __device__ __noinline__ void tc_lane_resume(tc_lane_state &s, tc_lane &c, const 
             // ---- barrier parameter update, skipAffine!=0 (:782-859) ----
             s.th_grad = s.norminf_grad < TC_MAX(1e-6, 1e0 * D.gradTolerance);
             s.th_eq = !hasG || s.norminf_eq < TC_MAX(1e-5, 1e0 * D.equalTolerance);
-            if (s.alphaPrimal > s.alphaMax_ / 2 && s.th_grad && s.th_eq) {
+            if (!D.skipAffine) {
+            } else if (s.alphaPrimal > s.alphaMax_ / 2 && s.th_grad && s.th_eq) {
                 const double r = sqrt(s.mu);   // pow(mu,.5) in the reference; sqrt is its correctly rounded value
                 s.mu *= TC_MIN(D.muFactorAggressive, r);
                 if (s.mu < s.muMin) s.mu = s.muMin;
@@ -312,17 +364,20 @@ __device__ __forceinline__ void tc_state_init(tc_lane_state &s, const tc_device_
 __device__ __forceinline__ void tc_lanes_round(tc_lane_state &s, tc_lane &c, const tc_device_image &P, double mu0,
                                                int maxIter, uint32_t big) {
     const bool alive = s.pc >= 0;
-    // 1. the first group this lane still misses for the function it waits on (128 = none)
-    int front = 128;
+    // 1. the first group this lane still misses for the function it waits on (TC_MAXGROUPS = none)
+    int front = TC_MAXGROUPS;
     if (alive) {
         const tc_func *f = P.funcs + s.want_fn;
-        const uint64_t n0 = f->parents[0] & ~c.st[0][0], n1 = f->parents[1] & ~c.st[0][1];
-        front = n0 ? __ffsll((long long)n0) - 1 : (n1 ? 64 + __ffsll((long long)n1) - 1 : 128);
+#pragma unroll
+        for (int w = TC_GW - 1; w >= 0; w--) {
+            const uint64_t miss = f->parents[w] & ~c.st[0][w];
+            if (miss) front = 64 * w + __ffsll((long long)miss) - 1;
+        }
     }
     // 2. lanes whose function is complete go on at once: copies first (one function at a
     //    time, its code is shared by the lanes that want it), then the solver code up to the
     //    lane's next get/copy
-    const bool ready = alive && front == 128;
+    const bool ready = alive && front == TC_MAXGROUPS;
     if (__any_sync(TC_FULL, ready)) {
         bool copying = ready && s.want_kind == TC_WANT_COPY;
         while (__any_sync(TC_FULL, copying)) {
@@ -344,8 +399,8 @@ __device__ __forceinline__ void tc_lanes_round(tc_lane_state &s, tc_lane &c, con
                 }
             }
             if (mine) {
-                c.st[0][0] &= ~f->children[0];
-                c.st[0][1] &= ~f->children[1];
+#pragma unroll
+                for (int w = 0; w < TC_GW; w++) c.st[0][w] &= ~f->children[w];
                 copying = false;
             }
         }
@@ -376,7 +431,7 @@ __device__ __forceinline__ void tc_lanes_round(tc_lane_state &s, tc_lane &c, con
     const unsigned vote = __ballot_sync(TC_FULL, need[0]);
     if (c.lane == 0) {
         atomicAdd(P.group_count + g, (unsigned long long)__popc(vote));
-        atomicAdd(P.group_count + 128 + g, 1ull);
+        atomicAdd(P.group_count + TC_MAXGROUPS + g, 1ull);
     }
 }
 
@@ -428,8 +483,8 @@ __device__ __forceinline__ void tc_queue_solve(tc_lane &c, const tc_device_image
             if (finished) {
                 status[inst] = s.status;
                 iter[inst] = s.iter;
-                P.group_status[inst] = fo->parents[0];
-                P.group_status[P.stride + inst] = fo->parents[1];
+#pragma unroll
+                for (int w = 0; w < TC_GW; w++) P.group_status[w * P.stride + inst] = fo->parents[w];
             }
             for (uint32_t k = 0; k < fo->io_cnt; k++) {                     // uniform loop, per-lane targets
                 const uint32_t w = __ldg(P.io + fo->io_off + k);
@@ -463,7 +518,8 @@ __device__ __forceinline__ void tc_queue_solve(tc_lane &c, const tc_device_image
             }
             if (take) {
                 inst = j;
-                c.st[0][0] = c.st[0][1] = 0;                                // every group is stale for the new instance
+#pragma unroll
+                for (int w = 0; w < TC_GW; w++) c.st[0][w] = 0;             // every group is stale for the new instance
                 tc_state_init(s, P, true, mu0, aeU0, aeEq0);
                 tc_lane_resume(s, c, P, mu0, maxIter);
             }

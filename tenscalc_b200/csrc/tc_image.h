@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include <vector_types.h>
 
-#define TC_MAGIC 0x3030324243540003LL
+#define TC_MAGIC 0x3030324243540004LL
 #define TC_CONST_BIT 0x40000000u   // io[] words (get/copy sources): constant-pool index
 #define TC_SLOT_MASK 0x3FFFFFFFu
 #define TC_NO_SLOT 0xFFFFFFFFu
@@ -14,6 +14,8 @@
 #define TC_RING 32                 // results in the per-lane ring         -- MUST match tape.py RING
 #define TC_MAXCONST 1024           // constant pool in shared memory       -- MUST match tape.py MAX_CONSTS
 #define TC_RING_DOUBLES (TC_RING * TC_BLOCK)
+#define TC_GW 4                    // 64-bit words of a dependency-group mask                -- MUST match tape.py GW
+#define TC_MAXGROUPS (64 * TC_GW)  // dependency groups per problem (groupStatus[] of the reference, one bit each)
 
 // tape cell = uint4 {op|flags|ring slot<<16, operand A, operand B, result offset}; see tape.py
 #define TC_F_ALATE (1u << 7)
@@ -41,7 +43,9 @@ enum tc_fn {
     FN_initDualEqX, FN_setAddEye2HessianU, FN_setAddEye2HessianEq, FN_getNorminf_Grad,
     FN_getNorminf_G, FN_getGapMinFMinLambda, FN_getCurvature, FN_getDirectionError,
     FN_getHessInertia, FN_getMaxAlphas_s, FN_setAlphaPrimal, FN_getMinF_s, FN_setAlphaDualEq,
-    FN_setAlphaDualIneq, FN_updatePrimalDual, FN_getJ, FN_getOutputs, FN_USER0
+    FN_setAlphaDualIneq, FN_updatePrimalDual, FN_getJ, FN_getOutputs,
+    FN_getMaxAlphas_a, FN_getMinF_a, FN_getRho,      // affine-scaling (Mehrotra) step, skipAffine=0 (ipmPD_CS.m:313-315,422-425)
+    FN_USER0
 };
 
 // opcodes = reference enum (lib/csparse/instructionsTableTypes.h:2-56)
@@ -54,8 +58,8 @@ enum tc_op {
 };
 
 struct tc_func {            // one set / get / copy function
-    uint64_t parents[2];    // dependency groups to (re)evaluate before reading
-    uint64_t children[2];   // dependency groups invalidated by writing
+    uint64_t parents[TC_GW];    // dependency groups to (re)evaluate before reading
+    uint64_t children[TC_GW];   // dependency groups invalidated by writing
     uint32_t io_off;        // into io[]: set = dst slots, get = src words, copy = (dst,src) pairs
     uint32_t io_cnt;
     uint64_t kind;
@@ -80,8 +84,8 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
                             // operand access is one 256-byte segment and a warp's whole working set sits
                             // in a handful of 2 MB pages (TLB reach) instead of being strided over the batch
     int64_t n_slots;
-    uint64_t *group_status; // [2][stride] lazy-evaluation flags per instance
-    unsigned long long *group_count; // [n_groups] instance-executions of every group (profiling)
+    uint64_t *group_status; // [TC_GW][stride] lazy-evaluation flags per scratchbook column
+    unsigned long long *group_count; // [2][TC_MAXGROUPS] instance- and warp-executions of every group (profiling)
     int64_t stride;         // padded batch (multiple of 32)
     int64_t batch;
     int32_t n_groups;
@@ -92,8 +96,17 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     unsigned long long *queue;    // next instance to hand out (reset before every solve)
     int64_t work_tiles;
     int32_t n_funcs;              // funcs[FN_USER0 .. n_funcs) are the user set functions
-    int32_t pad_;
+    int32_t phased;               // 1: the solve is a sequence of phase launches with compaction in between (tc_abi.cu)
+    // phased execution (compiled back end, warp driver): the solver loop's locals of every scratchbook
+    // column between two phase launches (tc_driver.cuh), the instance each column currently holds, and
+    // the number of columns [0, n_live) that hold unfinished instances
+    double *ps_d;                 // [TC_PS_ND][stride]
+    int32_t *ps_i;                // [TC_PS_NI][stride]
+    int32_t *orig;                // [stride] original instance whose state lives in the column, -1: none
+    int32_t *n_live;              // device scalar
 };
+#define TC_PS_ND 11
+#define TC_PS_NI 2
 
 // address of scratchbook slot `slot` of instance `inst`
 #define TC_M(P, slot, inst) \

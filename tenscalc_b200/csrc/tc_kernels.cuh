@@ -46,8 +46,8 @@ __device__ __forceinline__ void tc_lane_init(tc_lane &c, const tc_device_image &
     for (int t = 0; t < TC_TILES; t++) {
         const int64_t inst = tc_inst(t);
         c.mb[t] = &TC_M(P, 0, inst);
-        c.st[t][0] = P.group_status[inst];
-        c.st[t][1] = P.group_status[P.stride + inst];
+#pragma unroll
+        for (int w = 0; w < TC_GW; w++) c.st[t][w] = P.group_status[w * P.stride + inst];
     }
 }
 
@@ -55,8 +55,8 @@ __device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device
 #pragma unroll
     for (int t = 0; t < TC_TILES; t++) {
         const int64_t inst = tc_inst(t);
-        P.group_status[inst] = c.st[t][0];
-        P.group_status[P.stride + inst] = c.st[t][1];
+#pragma unroll
+        for (int w = 0; w < TC_GW; w++) P.group_status[w * P.stride + inst] = c.st[t][w];
     }
 }
 
@@ -66,35 +66,53 @@ __device__ __forceinline__ void tc_lane_finish(const tc_lane &c, const tc_device
 __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
                                                             double aeU, double aeEq,
                                                             int32_t *__restrict__ status,
-                                                            int32_t *__restrict__ iter) {
+                                                            int32_t *__restrict__ iter, int, int) {
     tc_lane c;
     c.sm = nullptr;
     c.consts = P.consts;
     c.tape = P.tape;
     c.lane = threadIdx.x & 31u;
     c.mb[0] = P.m_work + ((size_t)blockIdx.x * (size_t)P.n_slots) * TC_TILE + c.lane;
-    c.st[0][0] = c.st[0][1] = 0;
+#pragma unroll
+    for (int w = 0; w < TC_GW; w++) c.st[0][w] = 0;
     tc_queue_solve(c, P, mu0, maxIter, aeU, aeEq, status, iter);
 }
 #else
-// whole solve of ipmPD_CSsolver() for every instance of the batch; one launch per tc_solve
+// ipmPD_CSsolver() for every instance of the batch.  phase_iters == 0: the whole solve in one launch.  Otherwise
+// one PHASE of a phased solve (tc_driver.cuh, tc_abi.cu): at most phase_iters Newton iterations for the
+// instances in the columns [0, *P.n_live); results of the instances that finish go to status/iter at their
+// ORIGINAL index (P.orig: compaction moves instances between columns)
 __global__ void __launch_bounds__(TC_KBLOCK, TC_KMINBLOCKS) tc_solve_kernel(tc_device_image P, double mu0, int maxIter,
                                                             double aeU, double aeEq,
                                                             int32_t *__restrict__ status,
-                                                            int32_t *__restrict__ iter) {
+                                                            int32_t *__restrict__ iter, int phase_first,
+                                                            int phase_iters) {
+    const int64_t limit = phase_iters ? (int64_t)*P.n_live : P.batch;
+    if ((((int64_t)blockIdx.x * TC_KBLOCK) * TC_TILES) >= limit) return;     // no unfinished instance in this CTA's columns
     tc_lane c;
     tc_lane_init(c, P);
-    bool valid[TC_TILES];
+    bool valid[TC_TILES], done[TC_TILES];
     int st[TC_TILES], it[TC_TILES];
+    int64_t pos[TC_TILES];
 #pragma unroll
-    for (int t = 0; t < TC_TILES; t++) valid[t] = tc_inst(t) < P.batch;
+    for (int t = 0; t < TC_TILES; t++) {
+        pos[t] = tc_inst(t);
+        valid[t] = pos[t] < limit;
+    }
+#if defined(TC_DRIVER_LANES)
     tc_ipm_solve(c, P, valid, mu0, maxIter, aeU, aeEq, st, it);
+#pragma unroll
+    for (int t = 0; t < TC_TILES; t++) done[t] = valid[t];
+#else
+    tc_ipm_solve(c, P, valid, mu0, maxIter, aeU, aeEq, st, it, done, pos, phase_first, phase_iters);
+#endif
     tc_lane_finish(c, P);
 #pragma unroll
     for (int t = 0; t < TC_TILES; t++)
-        if (valid[t]) {
-            status[tc_inst(t)] = st[t];
-            iter[tc_inst(t)] = it[t];
+        if (done[t]) {
+            const int64_t o = phase_iters ? (int64_t)P.orig[pos[t]] : pos[t];
+            status[o] = st[t];
+            iter[o] = it[t];
         }
 }
 

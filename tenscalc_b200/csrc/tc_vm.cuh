@@ -49,7 +49,7 @@ struct tc_lane {
     const uint4 *tape;
     double *sm;            // shared memory of the CTA: result ring [TC_RING][TC_BLOCK], then constants
     unsigned lane;
-    uint64_t st[TC_TILES][2];   // groupStatus[] of every instance, one bit per group
+    uint64_t st[TC_TILES][TC_GW];   // groupStatus[] of every instance, one bit per group
 };
 
 #ifdef TC_COMPILED_GROUPS
@@ -256,7 +256,7 @@ __device__ __forceinline__ double tc_ldop(const tc_lane &c, int t, uint32_t w, b
 __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image &P, const tc_func *f,
                                                const bool (&pred)[TC_TILES]) {
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
+    for (int w = 0; w < TC_GW; w++) {
         uint64_t bits = f->parents[w];          // warp-uniform
         while (bits) {
             int b = __ffsll((long long)bits) - 1;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image
                 // reference's profiling counters, writeCfunctionpergroup.m:149-177,481-492)
                 if (c.lane == 0 && n) {
                     atomicAdd(P.group_count + 64 * w + b, (unsigned long long)n);
-                    atomicAdd(P.group_count + 128 + 64 * w + b, 1ull);
+                    atomicAdd(P.group_count + TC_MAXGROUPS + 64 * w + b, 1ull);
                 }
             }
 #pragma unroll
@@ -289,8 +289,8 @@ __device__ __forceinline__ void tc_invalidate(tc_lane &c, const tc_func *f, cons
 #pragma unroll
     for (int t = 0; t < TC_TILES; t++)
         if (pred[t]) {
-            c.st[t][0] &= ~f->children[0];
-            c.st[t][1] &= ~f->children[1];
+#pragma unroll
+            for (int w = 0; w < TC_GW; w++) c.st[t][w] &= ~f->children[w];
         }
 }
 

@@ -234,7 +234,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
 # per-problem module: chunk functions spread over part files + main.cu (dispatch, kernels, ABI)
 # --------------------------------------------------------------------------------------------
 EMITTER_VERSION = 1
-TCM_ABI = 1
+TCM_ABI = 2
 
 
 def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) -> List[Tuple[str, str]]:
@@ -359,12 +359,22 @@ __attribute__((visibility("default"))) int tcm_load(void) {{
     return (int)e;
 }}
 // ipmPD_CSsolver() for every instance of the batch: ONE launch, the Newton loop stays on the device
+// (phase_iters > 0: one phase of a phased solve -- at most that many Newton iterations, see tc_driver.cuh)
 __attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, double mu0, int maxIter, double aeU,
-                                                     double aeEq, int32_t *status, int32_t *iter, void *stream) {{
+                                                     double aeEq, int32_t *status, int32_t *iter, void *stream,
+                                                     int phase_first, int phase_iters) {{
     const unsigned grid = P->queue ? (unsigned)P->work_tiles : (unsigned)(P->stride / (TC_KBLOCK * TC_TILES));
     tc_solve_kernel<<<grid, TC_KBLOCK, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
-        *P, mu0, maxIter, aeU, aeEq, status, iter);
+        *P, mu0, maxIter, aeU, aeEq, status, iter, phase_first, phase_iters);
     return (int)cudaGetLastError();
+}}
+// 1: the module's driver parks/resumes the solver loop between phase launches (warp driver, one warp per CTA)
+__attribute__((visibility("default"))) int tcm_phased(void) {{
+#if defined(TC_DRIVER_LANES) || TC_LOCKSTEP > 1
+    return 0;
+#else
+    return 1;
+#endif
 }}
 // lazy evaluation of the parents of get function fn (classname_getOutputs)
 __attribute__((visibility("default"))) int tcm_eval(const tc_device_image *P, int fn, void *stream) {{

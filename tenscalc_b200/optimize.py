@@ -23,7 +23,7 @@ import numpy as np
 
 from . import tensor as T
 from .csparse import CSparse, CompiledProblem
-from .ipm_builder import build_ipm_timeslambda
+from .ipm_builder import build_ipm_pd, build_ipm_timeslambda
 from .tensor import Constraint, Tcalculus
 
 
@@ -49,7 +49,7 @@ def solver_defines(nU: int, nG: int, nF: int, *, gradTolerance: float = 1e-4, eq
                    skipAffine: bool = True, delta: int = 3, scaleInequalities: bool = True, scaleCost: float = 0.0,
                    scaleEqualities: bool = False, addEye2Hessian: bool = True, adjustAddEye2Hessian: bool = True,
                    useInertia: bool = False, addEye2HessianUtolerance: float = 1e-6, solverVerboseLevel: int = 1,
-                   **ignored) -> Dict[str, object]:
+                   smallerNewtonMatrix: bool = False, **ignored) -> Dict[str, object]:
     """the #define table cmex2optimizeCS hands to the C driver (lib/cmex2optimizeCS.m:303-331; defaults
     lib/private/parameters4all.m, parameters4optimize.m)"""
     return dict(
@@ -62,7 +62,7 @@ def solver_defines(nU: int, nG: int, nF: int, *, gradTolerance: float = 1e-4, eq
         setAddEye2Hessian=int(bool(addEye2Hessian)), adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)),
         useInertia=int(bool(useInertia)), muFactorAggressive=float(muFactorAggressive),
         muFactorConservative=float(muFactorConservative), delta=int(delta), skipAffine=int(bool(skipAffine)),
-        smallerNewtonMatrix=0, useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0,
+        smallerNewtonMatrix=int(bool(smallerNewtonMatrix)), useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0,
         profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
 
 
@@ -87,16 +87,24 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
                     addEye2HessianUtolerance: float = 1e-6, useLDL: bool = True,
                     smallerNewtonMatrix: bool = False, useUmfpack: bool = False,
                     sensitivityVariables: Sequence[Tcalculus] = (),
-                    solverVerboseLevel: int = 1, ordering=None, **ignored) -> GeneratedSolver:
+                    solverVerboseLevel: int = 1, ordering=None, algorithm: str = "ipmPD_CStimesLambda",
+                    **ignored) -> GeneratedSolver:
     # the reference's C generator hard-wires algorithm 3 and rejects the options below
     # (cmex2optimizeCS.m:83-93, ipmPD_CStimesLambda.m:31-48)
+    # ``algorithm`` selects the symbolic builder: "ipmPD_CStimesLambda" is what the shipped generator always
+    # uses (its `switch 3`, cmex2optimizeCS.m:83-93, which also forces skipAffine=true); "ipmPD_CS" is the
+    # builder of the same file's cases 1/2 (ipmPD_CS.m) with the affine-scaling (Mehrotra) step and the
+    # reduced Newton matrix that ipmPD_CSsolver.c supports (:576-665)
+    if algorithm not in ("ipmPD_CStimesLambda", "ipmPD_CS"):
+        raise ValueError("algorithm must be 'ipmPD_CStimesLambda' or 'ipmPD_CS'")
     if sensitivityVariables:
         raise NotImplementedError("sensitivityVariables: not implemented by ipmPD_CStimesLambda")
-    if smallerNewtonMatrix:
-        raise NotImplementedError("smallerNewtonMatrix=true: not implemented by ipmPD_CStimesLambda")
     if not useLDL or useUmfpack:
         raise NotImplementedError("useLDL=false/useUmfpack=true: not implemented by ipmPD_CStimesLambda")
-    skipAffine = True
+    if algorithm == "ipmPD_CStimesLambda":
+        if smallerNewtonMatrix:
+            raise NotImplementedError("smallerNewtonMatrix=true: not implemented by ipmPD_CStimesLambda")
+        skipAffine = True
 
     tab = T.table()
     code = CSparse(tab)
@@ -137,10 +145,16 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
     nu = [tab.new_set(f"nu__[{k}]") for k in range(len(G))]
     lam = [tab.new_set(f"lambda__[{k}]") for k in range(len(F))]
 
-    info = build_ipm_timeslambda(code, u, objective.e[()], F, G, lam, nu,
-                                 scaleInequalities=scaleInequalities, scaleCost=scaleCost,
-                                 addEye2Hessian=addEye2Hessian, useInertia=useInertia,
-                                 ordering=ordering)
+    if algorithm == "ipmPD_CS":
+        info = build_ipm_pd(code, u, objective.e[()], F, G, lam, nu,
+                            scaleInequalities=scaleInequalities, scaleCost=scaleCost,
+                            addEye2Hessian=addEye2Hessian, useInertia=useInertia, skipAffine=skipAffine,
+                            smallerNewtonMatrix=smallerNewtonMatrix, ordering=ordering)
+    else:
+        info = build_ipm_timeslambda(code, u, objective.e[()], F, G, lam, nu,
+                                     scaleInequalities=scaleInequalities, scaleCost=scaleCost,
+                                     addEye2Hessian=addEye2Hessian, useInertia=useInertia,
+                                     ordering=ordering)
 
     # ---- outputs (:337-355) --------------------------------------------------------------------
     is_struct = isinstance(outputExpressions, dict)
@@ -163,7 +177,7 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
                              scaleInequalities=scaleInequalities, scaleCost=scaleCost, scaleEqualities=scaleEqualities,
                              addEye2Hessian=addEye2Hessian, adjustAddEye2Hessian=adjustAddEye2Hessian,
                              useInertia=useInertia, addEye2HessianUtolerance=addEye2HessianUtolerance,
-                             solverVerboseLevel=solverVerboseLevel)
+                             solverVerboseLevel=solverVerboseLevel, smallerNewtonMatrix=smallerNewtonMatrix)
     problem = code.compile(defines)
     fac = info["factor"]
     from .ordering import DEFAULT as default_ordering

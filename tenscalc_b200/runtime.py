@@ -43,6 +43,8 @@ ABI = [
     ("tc_solve", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p, _dp]),
     ("tc_solve_async", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p]),
     ("tc_solve_device", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p]),
+    ("tc_set_phased", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("tc_set_phases", ctypes.c_int, [ctypes.c_void_p, _ip, ctypes.c_int]),
     ("tc_get_outputs", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     ("tc_get_outputs_device", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     ("tc_synchronize", ctypes.c_int, [ctypes.c_void_p]),
@@ -113,7 +115,7 @@ class BatchedSolver:
         :func:`tenscalc_b200.build.build_module` emits and compiles (built on first use when it is
         not in ``tenscalc_b200/_gen/``, like cmex2optimizeCS compiles its C at generation time);
         ``backend="tape"`` runs the generic tape interpreter (no per-problem compilation).
-        ``module_opts`` are emitter options (``lockstep``, ``max_refs``, ``max_live``), see
+        ``module_opts`` are emitter options (``lockstep``, ``max_refs``, ``max_loads``, ``driver``), see
         :func:`tenscalc_b200.emit_cuda.emit_module`."""
         if backend not in ("compiled", "tape"):
             raise ValueError("backend must be 'compiled' or 'tape'")
@@ -256,6 +258,13 @@ class BatchedSolver:
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
         fn = self._lib.tc_get_outputs_device if device else self._lib.tc_get_outputs
         _check(fn(self._h, arr))
+
+    def set_phased(self, on: bool = True, phases: Sequence[int] = ()) -> None:
+        """phased solve on/off (csrc/tc_driver.cuh); ``phases``: iteration budget of phase 0,1,... (last repeats)"""
+        _check(self._lib.tc_set_phased(self._h, int(bool(on))))
+        if on:
+            arr = (ctypes.c_int32 * max(len(phases), 1))(*phases)
+            _check(self._lib.tc_set_phases(self._h, arr, len(phases)))
 
     def stream_ptr(self) -> int:
         return int(self._lib.tc_stream(self._h) or 0)

@@ -48,7 +48,7 @@ from . import itable as it
 from .csparse import CompiledProblem
 from .optimize import GeneratedSolver
 
-MAGIC = 0x3030324243540003  # "\x03\0TCB200" little-endian tag + format version
+MAGIC = 0x3030324243540004  # "\x03\0TCB200" little-endian tag + format version
 CONST_BIT = 1 << 30         # io[] words only (get/copy sources): constant-pool index
 NO_SLOT = 0xFFFFFFFF
 
@@ -82,21 +82,52 @@ FN = {name: k for k, name in enumerate([
     "initDualEqX__", "setAddEye2HessianU__", "setAddEye2HessianEq__", "getNorminf_Grad__",
     "getNorminf_G__", "getGapMinFMinLambda__", "getCurvature__", "getDirectionError__",
     "getHessInertia__", "getMaxAlphas_s__", "setAlphaPrimal__", "getMinF_s__", "setAlphaDualEq__",
-    "setAlphaDualIneq__", "updatePrimalDual__", "getJ__", "getOutputs"])}
+    "setAlphaDualIneq__", "updatePrimalDual__", "getJ__", "getOutputs",
+    "getMaxAlphas_a__", "getMinF_a__", "getRho__"])}
 FN_USER0 = len(FN)
 KIND_NONE, KIND_SET, KIND_GET, KIND_COPY = 0, 1, 2, 3
 
 
-def _mask128(groups) -> Tuple[int, int]:
-    lo = hi = 0
+GW = 4                      # 64-bit words of a dependency-group mask -- MUST match TC_GW
+MAX_GROUPS = 64 * GW
+
+
+def _mask(groups) -> List[int]:
+    words = [0] * GW
     for g in groups:
-        if g >= 128:
-            raise ValueError("more than 128 dependency groups")
-        if g < 64:
-            lo |= 1 << g
-        else:
-            hi |= 1 << (g - 64)
-    return lo, hi
+        if g >= MAX_GROUPS:
+            raise ValueError(f"more than {MAX_GROUPS} dependency groups")
+        words[g >> 6] |= 1 << (g & 63)
+    return words
+
+
+def persistent_state(pr: CompiledProblem):
+    """What must move with an instance when the phased solve compacts the unfinished instances
+    (csrc/tc_driver.cuh, tc_abi.cu): the slots of every variable (``I_set``: destinations of set functions
+    and copies) and of the values that STATIC groups -- groups no solver-side set or copy invalidates,
+    i.e. parameter-only subexpressions -- export to other groups, gets or copies.  Returns
+    (sorted slot list, static group ids)."""
+    tab = pr.tab
+    dynamic = set()
+    for s in pr.sets.values():
+        if s.kind == "solver":
+            dynamic.update(s.children)
+    for c in pr.copies.values():
+        dynamic.update(c.children)
+    static = [g for g in range(len(pr.groups)) if g not in dynamic]
+    ext = set()
+    for g in pr.gets.values():
+        ext.update(x for s in g.sources for x in s if x is not None)
+    for c in pr.copies.values():
+        ext.update(c.src)
+    for i, gi in pr.group_of.items():
+        for o in tab.operands[i]:
+            if pr.group_of.get(o, -1) != gi:
+                ext.add(o)
+    slots = {int(pr.slot[i]) for i in range(len(tab)) if tab.types[i] == it.I_set and pr.slot[i] >= 0}
+    for g in static:
+        slots.update(int(pr.slot[i]) for i in pr.groups[g] if i in ext and pr.slot[i] >= 0)
+    return sorted(slots), static
 
 
 def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
@@ -286,19 +317,17 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
         while len(cells) % bundle:
             cells.append([OP_NOP | F_ALATE | F_BLATE, RING_BYTES, RING_BYTES, 0])
         group_start.append(len(cells))
-    if len(consts) > MAX_CONSTS:
-        raise ValueError(f"{len(consts)} distinct constants exceed the shared-memory constant pool ({MAX_CONSTS})")
+    # more than MAX_CONSTS distinct constants: fine for the compiled back end (constants are immediates there);
+    # the interpreter keeps the pool in shared memory and refuses such an image at solve time (tc_abi.cu)
 
     # ---- function table ------------------------------------------------------------------------
     user_sets = [s for s in pr.sets.values() if s.kind in ("parameter", "variable")]
     n_funcs = FN_USER0 + len(user_sets)
-    funcs = np.zeros((n_funcs, 6), dtype=np.uint64)   # parents lo/hi, children lo/hi, io_off|io_cnt<<32, kind
+    funcs = np.zeros((n_funcs, 2 * GW + 2), dtype=np.uint64)   # parents[GW], children[GW], io_off|io_cnt<<32, kind
     io: List[int] = []
 
     def put(fid: int, kind: int, parents, children, words: List[int]) -> None:
-        plo, phi = _mask128(parents)
-        clo, chi = _mask128(children)
-        funcs[fid] = (plo, phi, clo, chi, len(io) | (len(words) << 32), kind)
+        funcs[fid] = tuple(_mask(parents)) + tuple(_mask(children)) + (len(io) | (len(words) << 32), kind)
         io.extend(words)
 
     def src_word(x) -> int:
@@ -327,7 +356,10 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
         set_fids.append(FN_USER0 + k)
     out_sizes = [int(np.prod(s)) if s else 1 for _, s in gen.outputs]
 
-    return dict(tape=np.asarray(cells, dtype=np.uint32).reshape(-1, 4),
+    persist, static = persistent_state(pr)
+    return dict(persist=np.asarray(persist if persist else [0], dtype=np.uint32), n_persist=len(persist),
+                static_mask=_mask(static),
+                tape=np.asarray(cells, dtype=np.uint32).reshape(-1, 4),
                 group_start=np.asarray(group_start, dtype=np.uint32),
                 consts=np.asarray(consts if consts else [0.0], dtype=np.float64), funcs=funcs,
                 io=np.asarray(io if io else [0], dtype=np.uint32),
@@ -342,7 +374,8 @@ def serialize(gen: GeneratedSolver) -> bytes:
     ih[0] = MAGIC
     ih[1:9] = (gen.problem.n_slots, len(gen.problem.groups), len(L["funcs"]), len(L["set_fids"]),
                len(L["out_sizes"]), len(L["tape"]), len(L["consts"]), len(L["io"]))
-    ih[9:11] = (RING, BUNDLE)
+    ih[9:13] = (RING, BUNDLE, L["n_persist"], GW)
+    ih[32:32 + GW] = np.asarray(L["static_mask"], dtype=np.uint64).view(np.int64)
     ih[16:19] = (d["nU"], d["nG"], d["nF"])
     ih[19:27] = (d["scaleCost"], d["scaleInequalities"], d["coupledAlphas"], d["setAddEye2Hessian"],
                  d["adjustAddEye2Hessian"], d["useInertia"], d["skipAffine"], d["delta"])
@@ -354,6 +387,6 @@ def serialize(gen: GeneratedSolver) -> bytes:
         return b + b"\0" * (-len(b) % 16)
 
     parts = [ih.tobytes(), dh.tobytes()]
-    for key in ("group_start", "tape", "consts", "funcs", "io", "set_fids", "out_sizes"):
+    for key in ("group_start", "tape", "consts", "funcs", "io", "set_fids", "out_sizes", "persist"):
         parts.append(pad16(np.ascontiguousarray(L[key]).tobytes()))
     return b"".join(parts)

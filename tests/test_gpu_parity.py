@@ -16,8 +16,11 @@ pytestmark = pytest.mark.gpu
 # extra emitter options for the compiled back end, e.g. TC_MODULE_OPTS='{"driver": "lanes"}'
 MODULE_OPTS = __import__("json").loads(__import__("os").environ.get("TC_MODULE_OPTS", "{}"))
 
+AFFINE = {"algorithm": "ipmPD_CS", "skipAffine": False}     # Mehrotra predictor (ipmPD_CSsolver.c:576-665; builder ipmPD_CS.m)
 CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_quadcopter", 96, {}),
-         ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})]
+         ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True}),
+         ("sls", 512, AFFINE), ("mpc_dcmotor", 512, AFFINE), ("mpc_dcmotor", 512, {**AFFINE, "smallerNewtonMatrix": True}),
+         ("mpc_quadcopter", 256, {"T_": 20, **AFFINE})]
 
 
 def _oracle(gen, name):
@@ -102,7 +105,8 @@ def test_tiles_option_is_bit_identical():
 
 
 @pytest.mark.parametrize("driver", ["lanes", "queue"])
-@pytest.mark.parametrize("name,batch,kw", [("sls", 5000, {}), ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True})])
+@pytest.mark.parametrize("name,batch,kw", [("sls", 5000, {}), ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True}),
+                                           ("sls", 3000, AFFINE)])
 def test_lane_decoupled_driver_parity(name, batch, kw, driver):
     """emitter option driver="lanes" (csrc/tc_driver_lanes.cuh: every lane runs the reference's loop as a
     coroutine) and driver="queue" (the same, with resident warps pulling instances from a work queue into
@@ -181,3 +185,34 @@ def test_queue_driver_set_then_get_outputs_without_solve():
         obj.close()
     for a, b in zip(*res):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,batch,kw,phases", [("sls", 5000, {}, ()), ("sls", 33, {}, (1,)), ("mpc_dcmotor", 4097, {}, (3, 1, 2)),
+                                                  ("mpc_quadcopter", 1000, {"T_": 20, "useInertia": True}, ()),
+                                                  ("mpc_dcmotor", 2000, AFFINE, (2,))])
+def test_phased_solve_is_bit_identical_to_the_single_launch_solve(name, batch, kw, phases):
+    """the phased solve (phases of a few Newton iterations, unfinished instances compacted into full warps in
+    between, everything moved home at the end: csrc/tc_driver.cuh, tc_abi.cu) gives exactly the status, iteration
+    counts and outputs of the single-launch solve -- also after a set_<parameter> + getOutputs without a new solve"""
+    gen, args = generated(name, **kw)
+    P, V = problems.synthetic_inputs(name, gen, batch, seed=21)
+    res = []
+    for phased in (False, True):
+        obj = _solve(gen, args, P, V, batch)
+        obj.set_phased(phased, phases)
+        st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+        y = obj.getOutputs()
+        y = list(y.values()) if isinstance(y, dict) else y
+        first = gen.parameters[0][0]
+        getattr(obj, "setP_" + first)(np.asarray(P[first]) * 1.25)       # outputs re-evaluated at the optimum
+        y2 = obj.getOutputs()
+        y2 = list(y2.values()) if isinstance(y2, dict) else y2
+        st2, it2, _ = obj.solve(args["mu0"], args["maxIter"], -1)         # and a second solve on the same handle
+        res.append((st, it, y, y2, st2, it2))
+        obj.close()
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    for u, v in list(zip(a[2], b[2])) + list(zip(a[3], b[3])):
+        assert np.array_equal(u, v, equal_nan=True)
+    assert len(np.unique(a[1])) > 1          # instances really finish at different iterations
