@@ -60,11 +60,12 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per core in the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=3,
+    ap.add_argument("--pipeline", type=int, default=5,
                     help="solver handles kept in flight (own stream + scratchbook each): the straggler tail of "
                          "step k overlaps the bulk of steps k+1.. ; 1 = strictly one batch at a time")
     ap.add_argument("--driver", default="", choices=["", "warp", "lanes"],
                     help="device driver of the compiled back end (default: the emitter's default)")
+    ap.add_argument("--mopts", default="", help="emitter options of the compiled module, e.g. lockstep=4,max_loads=64")
     ap.add_argument("--parity", type=int, default=4096,
                     help="benchmarked instances re-solved by the CPU oracle after the timed region (0: skip)")
     ap.add_argument("--no-strong", action="store_true",
@@ -262,6 +263,17 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _mopts(args):
+    """emitter options of the compiled module from --driver / --mopts (integers unless quoted names)"""
+    if args.backend != "compiled":
+        return {}
+    o = dict(driver=args.driver) if args.driver else {}
+    for kv in filter(None, args.mopts.split(",")):
+        k, v = kv.split("=")
+        o[k] = int(v) if v.lstrip("-").isdigit() else v
+    return o
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -332,7 +344,7 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
     # launches and the few instances that need hundreds of Newton iterations (the tail of one
     # batch) run next to the bulk of the following batches instead of holding the GPU alone
     depth = max(1, min(args.pipeline, K))
-    mopts = dict(driver=args.driver) if args.driver and args.backend == "compiled" else {}
+    mopts = _mopts(args)
     objs = [gen(B, device=local_rank, backend=args.backend, **mopts) for _ in range(depth)]
     obj = objs[0]
     assert obj.has_module() == (args.backend == "compiled")
@@ -517,7 +529,7 @@ def run_ours(args, rank, local_rank, world):
         if args.backend == "compiled":     # bytes the emitted code loads/stores (after per-chunk register reuse)
             from tenscalc_b200.build import default_module_opts
             from tenscalc_b200.emit_cuda import emit_module
-            per_group = emit_module(gen, **default_module_opts(gen))[1]["per_group"]
+            per_group = emit_module(gen, **{**default_module_opts(gen, **_mopts(args)), **_mopts(args)})[1]["per_group"]
             issued = np.array([8.0 * (g["loads"] + g["stores"]) for g in per_group])
         else:
             issued = tables["vm_bytes"]

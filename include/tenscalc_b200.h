@@ -98,6 +98,16 @@ int tc_set_phases(tc_solver *s, const int32_t *iterations_per_phase, int n);
 int tc_get_outputs(tc_solver *s, double *const *y);
 int tc_get_outputs_device(tc_solver *s, double *const *d_y);
 
+/* Device-resident warm start of a receding-horizon loop.  The reference's MPC examples feed outputs of
+ * one solve back as the initial primal values of the next -- `out=getOutputs(obj); ...
+ * setV_x(obj,out.xWarm); setV_u(obj,out.uWarm)` (examples/mpcmhe/mpc_dcmotor.m:108-126,192-225; lib/Tmpc.m) --
+ * through host arrays.  tc_feedback does the same without leaving the device: it evaluates the output
+ * expressions (the lazy evaluation of <class>_getOutputs) and writes output out_index[k] into set function
+ * set_index[k] for every pair, invalidating what depends on it exactly as tc_set does.  All outputs are read
+ * before anything is written (an output is typically a shifted view of the variable it feeds), the values are
+ * exact copies, and tc_output_size(out_index[k]) must equal tc_set_size(set_index[k]). */
+int tc_feedback(tc_solver *s, int n_pairs, const int32_t *out_index, const int32_t *set_index);
+
 /* Stream control and measurement hooks used by bench.py. */
 int tc_synchronize(tc_solver *s);
 void *tc_stream(tc_solver *s);                 /* cudaStream_t of the handle */
@@ -112,6 +122,35 @@ int tc_group_counts(tc_solver *s, int64_t *counts, int reset);
 /* same, counting WARP-executions: counts[g]*32 / tc_group_counts[g] is the lane occupancy of group g */
 int tc_group_warp_counts(tc_solver *s, int64_t *counts, int reset);
 const char *tc_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense path: box-constrained dense least squares  min ||A x - b||^2/N  s.t. lo <= x <= hi  (BASELINE.json
+ * config 5: N=4000, n=256; the problem class of examples/sls.m:136-166, whose generated class exposes
+ * setP_A, setP_b, setV_x, solve, getOutputs -> {J, x}).  Same three operations as above on a handle that owns
+ * a batch; the scalar instruction list is replaced by dense kernels (FP64 tensor-core Gram matrix and LDL'
+ * trailing updates, csrc/tc_dense.cu) while the solver loop is ipmPD_CSsolver.c's.  n must be 8, 16, 32, 64,
+ * 128 or 256.  Layouts: A double[batch][N*n] (every instance column-major, like the MATLAB array A(:,:,k)),
+ * b double[batch][N], x double[batch][n].  on_device != 0: the pointer is device memory; A and b are then
+ * BORROWED (no copy) and must stay valid until the next tc_dense_solve* has been enqueued. */
+typedef struct tc_dense tc_dense;
+int tc_dense_create(tc_dense **out, int64_t N, int64_t n, int64_t batch, double lo, double hi, int device);
+int tc_dense_destroy(tc_dense *s);
+int tc_dense_set_A(tc_dense *s, const double *A, int on_device);   /* <class>_set_A */
+int tc_dense_set_b(tc_dense *s, const double *b, int on_device);   /* <class>_set_b */
+int tc_dense_set_x(tc_dense *s, const double *x, int on_device);   /* <class>_set_x (primal initial value) */
+/* ipmPD_CSsolver for every instance (arguments by pointer as in lib/ipmPD_CSsolver.c:132-141) */
+int tc_dense_solve(tc_dense *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+                   const double *addEye2Hessian, int32_t *status, int32_t *iter, double *time);
+int tc_dense_solve_async(tc_dense *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
+                         const double *addEye2Hessian);
+/* <class>_getOutputs: J double[batch], x double[batch][n]; status/iter int32[batch] or NULL */
+int tc_dense_get_outputs(tc_dense *s, double *J, double *x, int32_t *status, int32_t *iter, int on_device);
+int tc_dense_synchronize(tc_dense *s);
+void *tc_dense_stream(tc_dense *s);
+/* measurement hooks: CUDA-event times of the last solve (Gram kernel, Newton-loop kernel); kernel launches and
+ * FP64 tensor-core flops issued by the LDL' trailing updates since creation */
+int tc_dense_times_ms(tc_dense *s, float *gram_ms, float *solve_ms);
+int tc_dense_counters(tc_dense *s, int64_t *launches, int64_t *dmma_flops);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ from concurrent.futures import ProcessPoolExecutor
 
 AFFINE = {"algorithm": "ipmPD_CS", "skipAffine": False}           # Mehrotra predictor (ipmPD_CSsolver.c:576-665, ipmPD_CS.m)
 AFFINE_SMALL = {**AFFINE, "smallerNewtonMatrix": True}            # + reduced Newton matrix (ipmPD_CS.m:242-351)
-CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}),
+CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}), ("isa_probe", {}),
            ("mpc_quadcopter", {"T_": 20, "useInertia": True}),    # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
            ("sls", AFFINE), ("mpc_dcmotor", AFFINE), ("mpc_dcmotor", AFFINE_SMALL),
            ("mpc_quadcopter", {"T_": 20, **AFFINE})]
@@ -28,7 +28,15 @@ def _one(args):
     return name, kind + opt + variant, so, time.time() - t
 
 
+# dense least squares (config 5, oracle/dense_ls.c): (N, n, lo, hi) of tests/test_dense.py and bench.py --workload dense_ls
+DENSE = [(100, 8, 0.0, .05), (400, 32, -1.0, 1.0), (4000, 256, -1.0, 1.0)]
+
+
 def build_all(kinds=("ref", "port"), configs=CONFIGS, workers=4, extra=True):
+    from oracle.dense_oracle import DenseOracle
+    for N, n, lo, hi in DENSE:
+        for k in kinds:
+            print("oracle dense_ls", N, n, k, DenseOracle(N, n, lo, hi, k).build())
     jobs = [(n, kw, k, "-O1", "") for n, kw in configs for k in kinds]
     if extra:
         jobs += [(n, kw, kinds[0], opt, var) for n, kw, opt, var in EXTRA]

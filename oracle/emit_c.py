@@ -63,9 +63,8 @@ def statement(tab: it.InstructionTable, i: int, slot: np.ndarray) -> str:
     if t == it.I_sum:
         return f"\t{r}=" + "".join(("+" if s > 0 else "-") + x for s, x in zip(p, o)) + ";\n"   # :964-968
     if t == it.I_sumprod:
-        m = int(p[0])
-        assert len(o) <= it.MAX_TERMS_PERLINE
-        return f"\t{r}=" + "+".join("*".join(o[k:k + m]) for k in range(0, len(o), m)) + ";\n"  # :1007-1029
+        lines = it.sumprod_lines(int(p[0]), o)                                 # :1007-1029 (line breaks :1019-1026)
+        return f"\t{r}={lines[0]};\n" + "".join(f"\t{r}+={ln};\n" for ln in lines[1:])
     if t == it.I_plus_minus_dot_div:
         return f"\t{r}=({o[0]}-({pairs(o[2:])}))/{o[1]};\n"                    # :1081-1098
     if t == it.I_minus_dot_div:

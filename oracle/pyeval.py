@@ -59,13 +59,17 @@ def eval_instruction(tab: it.InstructionTable, i: int, v: Dict[int, np.ndarray],
         return acc
     if t == it.I_sumprod:                                          # :1007-1029
         m = int(p[0])
-        acc = None
-        for k in range(0, len(o), m):
-            pr = v[o[k]]
-            for x in o[k + 1:k + m]:
-                pr = pr * v[x]
-            acc = pr if acc is None else acc + pr
-        return acc
+        per = m * -(-it.MAX_TERMS_PERLINE // m)                    # operands per emitted line (:1019-1026)
+        total = None
+        for k0 in range(0, len(o), per):                           # m[d]=line1; m[d]+=line2; ...
+            acc = None
+            for k in range(k0, min(k0 + per, len(o)), m):
+                pr = v[o[k]]
+                for x in o[k + 1:k + m]:
+                    pr = pr * v[x]
+                acc = pr if acc is None else acc + pr
+            total = acc if total is None else total + acc
+        return total
     if t == it.I_plus_minus_dot_div:                               # :1081-1098
         return (v[o[0]] - _dot_pairs(v, o[2:])) / v[o[1]]
     if t == it.I_minus_dot_div:                                    # :1106-1121

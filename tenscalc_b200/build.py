@@ -85,13 +85,18 @@ def _toolchain_tag(emit_opts: dict) -> str:
     return h.hexdigest()[:8]
 
 
-def default_module_opts(gen) -> dict:
+def default_module_opts(gen, **given) -> dict:
     """launch shape per problem size (measured on B200, profiles/): small scratchbooks (mpc_dcmotor,
-    sls) run fastest with many light warps -- 24 warps/SM at 80 registers, 28 operands per chunk --
-    large ones (mpc_quadcopter, l1l2) with 8 warps/SM at 255 registers and 96 operands per chunk"""
-    if gen.problem.n_slots <= 8192:
-        return dict(warps_per_sm=24, max_loads=28)
-    return {}
+    sls) run fastest with many light warps -- 24 warps/SM at 80 registers, 28 operands per chunk.  Large
+    ones (mpc_quadcopter, l1l2) run 12 warps/SM at 168 registers with 72 operands per chunk, the warps
+    grouped in CTAs of 4 that walk the straight-line code in lockstep (one barrier per chunk), so that the
+    instruction stream -- the largest stall of these kernels is instruction fetch -- is fetched once per
+    CTA: +17 % over 8 independent warps/SM at 255 registers (profiles/r02i_*).  Lockstep needs the
+    warp-synchronous driver with one instance per lane."""
+    solo = given.get("driver", "warp") != "warp" or given.get("tiles", 1) != 1
+    if gen.problem.n_slots <= 8192:        # lockstep 8: mpc_dcmotor +13 %, sls +7 % (profiles/r02j_*)
+        return dict(warps_per_sm=24, max_loads=28, **({} if solo else dict(lockstep=8)))
+    return {} if solo else dict(lockstep=4, warps_per_sm=12, max_loads=72)
 
 
 def module_path(gen, **emit_opts) -> str:
@@ -105,7 +110,7 @@ def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0,
     import time
     from concurrent.futures import ThreadPoolExecutor
     from .emit_cuda import emit_module
-    emit_opts = {**default_module_opts(gen), **emit_opts}
+    emit_opts = {**default_module_opts(gen, **emit_opts), **emit_opts}
     so = module_path(gen, **emit_opts)
     if not force and os.path.exists(so):
         return so

@@ -219,6 +219,8 @@ struct tc_solver {
     int32_t *d_status = nullptr, *d_iter = nullptr;
     unsigned long long *d_sum = nullptr;
     double *d_stage = nullptr;           // staging for host<->device I/O
+    double *d_feedback = nullptr;        // staging of tc_feedback
+    size_t feedback_bytes = 0;
     size_t stage_bytes = 0;
     int64_t n_slots = 0, launches = 0;
     float last_ms = 0.f;
@@ -685,6 +687,48 @@ int tc_get_outputs(tc_solver *s, double *const *y) {
                                 s->stream));
     }
     TC_CUDA(cudaStreamSynchronize(s->stream));
+    return (int)cudaGetLastError();
+}
+
+int tc_feedback(tc_solver *s, int n_pairs, const int32_t *out_index, const int32_t *set_index) {
+    if (!s || n_pairs < 0 || (n_pairs > 0 && (!out_index || !set_index))) return TC_EINVAL;
+    size_t total = 0;
+    for (int k = 0; k < n_pairs; k++) {
+        if (out_index[k] < 0 || out_index[k] >= (int)s->out_sizes.size() || set_index[k] < 0 ||
+            set_index[k] >= (int)s->set_fids.size())
+            return TC_EINVAL;
+        if (s->out_sizes[out_index[k]] != s->funcs[s->set_fids[set_index[k]]].io_cnt) return TC_EINVAL;
+        total += s->out_sizes[out_index[k]];
+    }
+    if (total == 0) return 0;
+    TC_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = total * (size_t)s->batch * sizeof(double);
+    if (bytes > s->feedback_bytes) {                       // staging [pair][batch][n], grown on demand
+        void *d = nullptr;
+        TC_CUDA(cudaStreamSynchronize(s->stream));
+        TC_CUDA(cudaMalloc(&d, bytes));
+        s->allocs.push_back(d);                            // (the smaller buffer is released with the handle)
+        s->d_feedback = (double *)d;
+        s->feedback_bytes = bytes;
+    }
+    TC_CUDA((cudaError_t)tc_launch_eval(s, (int)FN_getOutputs));
+    double *stage = s->d_feedback;
+    for (int k = 0; k < n_pairs; k++) {                    // read every output first ...
+        const uint32_t n = s->out_sizes[out_index[k]];
+        if (n == 0) continue;
+        dim3 grid((unsigned)((s->batch + 31) / 32), (n + 31) / 32), block(32, 8);
+        tc_gather_kernel<<<grid, block, 0, s->stream>>>(s->img, s->out_offs[out_index[k]], n, stage);
+        s->launches++;
+        stage += (size_t)n * s->batch;
+    }
+    stage = s->d_feedback;
+    for (int k = 0; k < n_pairs; k++) {                    // ... then write the set functions
+        const uint32_t n = s->out_sizes[out_index[k]];
+        if (n == 0) continue;
+        int rc = tc_set_device(s, set_index[k], stage, n);
+        if (rc) return rc;
+        stage += (size_t)n * s->batch;
+    }
     return (int)cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ from .itable import InstructionTable, Id
 class Differentiator:
     def __init__(self, tab: InstructionTable, wrt: Iterable[int], sqrt_by_division: bool = True):
         self.tab = tab
-        self.sqrt_by_division = sqrt_by_division
+        self.sqrt_by_division = sqrt_by_division and getattr(tab, "sqrt_by_division", True)
         self.wrt = set(wrt)
         self._memo: Dict[int, Dict[int, int]] = {}
         self._one = tab.const(1.0)

@@ -36,7 +36,6 @@ from . import itable as it
 from .csparse import CompiledProblem
 
 TILE = 32                  # lanes per scratchbook tile -- MUST match TC_TILE
-MAX_TERMS = it.MAX_TERMS_PERLINE
 
 
 def _lit(v: float) -> str:
@@ -55,10 +54,12 @@ def expression(t: int, p: Sequence[float], o: List[str], r: str) -> str:
     if t == it.I_sum:                                                         # :964-968
         return f"const double {r}=" + "".join(("+" if s > 0 else "-") + x for s, x in zip(p, o)) + ";"
     if t == it.I_sumprod:                                                     # :1007-1029
-        m = int(p[0])
-        if len(o) > MAX_TERMS:
-            raise NotImplementedError("sumprod with more than one emitted line")
-        return f"const double {r}=" + "+".join("*".join(o[k:k + m]) for k in range(0, len(o), m)) + ";"
+        lines = it.sumprod_lines(int(p[0]), o)
+        if len(lines) == 1:
+            return f"const double {r}={lines[0]};"
+        # more than MAX_TERMS_PERLINE factors: the reference breaks the statement, m[d]=line1; m[d]+=line2; ...
+        # -- every line is summed on its own and then added to the running value (:1019-1026)
+        return f"double {r}={lines[0]};" + "".join(f" {r}+={ln};" for ln in lines[1:])
     if t == it.I_plus_minus_dot_div:                                          # :1081-1098
         return f"const double {r}=TC_DIV(({o[0]}-({pairs(o[2:])})),{o[1]});"
     if t == it.I_minus_dot_div:                                               # :1106-1121
@@ -148,7 +149,7 @@ def chunk_group(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_
 
 def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                max_loads: int = 96, prefetch: int = 1, merge: int = 1,
-               assume_global: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+               assume_global: int = 0, barrier: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
     """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics"""
     tab, slot = pr.tab, pr.slot
     members = pr.groups[g]
@@ -211,6 +212,8 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             name, loads, stores, lines = bodies[k]
             # one pass over the chunk's code per tile of the warp: the second pass runs out of the
             # instruction cache (TC_TILE_LOOP / TC_MT are defined in the module header)
+            if barrier:            # lockstep: the warps of the CTA enter every chunk together, so its code is
+                src.append("__syncthreads();")   # fetched once per CTA while it is still in the instruction caches
             src.append("TC_TILE_LOOP {")
             src.append("double *__restrict__ mt = TC_MT;")
             src += [f"const double v{q}=mt[{int(slot[q]) * TILE}];" for q in loads]
@@ -273,7 +276,7 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0)
     per_group = []
     for g in range(len(pr.groups)):
-        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global)
+        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global, barrier=int(lockstep > 1))
         funcs += fs
         group_calls.append([n for n, _ in fs])
         per_group.append(st)
@@ -324,7 +327,7 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
                f"#define TC_KMINBLOCKS {warps_per_sm // lockstep}\n"]
     m += [f"__device__ void {n}(double *__restrict__ m, unsigned mask);\n" for n, _ in funcs]
     m.append("__device__ __noinline__ void tcm_group(int g, double *m, unsigned mask) {\n    switch (g) {\n")
-    bar = " __syncthreads();" if lockstep > 1 else ""
+    bar = ""                       # lockstep: the barriers sit in front of every chunk (emit_group)
     for g, calls in enumerate(group_calls):
         m.append(f"    case {g}:" + "".join(f" {n}(m, mask);{bar}" for n in calls) + " break;\n")
     m.append("    }\n}\n")
@@ -370,7 +373,7 @@ __attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, d
 }}
 // 1: the module's driver parks/resumes the solver loop between phase launches (warp driver, one warp per CTA)
 __attribute__((visibility("default"))) int tcm_phased(void) {{
-#if defined(TC_DRIVER_LANES) || TC_LOCKSTEP > 1
+#if defined(TC_DRIVER_LANES)
     return 0;
 #else
     return 1;

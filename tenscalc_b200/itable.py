@@ -137,8 +137,20 @@ _UNARY_DERIV = {
 
 # longest product list the reference emitter prints on one C line; longer lists
 # get split into `m[r]=...; m[r]+=...;` which changes the association order
-# (instructionsTableUTHash.c:173,1013-1022).  We never create longer ones.
+# (instructionsTableUTHash.c:173,1013-1022).  The front end never creates longer ones unless
+# InstructionTable.split_long is switched off (then, like MATLAB's csparse, it leaves the line breaks to the
+# emitters); tables read from .cg files may hold them.
 MAX_TERMS_PERLINE = 100
+
+
+def sumprod_lines(m: int, o):
+    """The emitted statement(s) of ``I_sumprod [m, s]`` over operand expressions ``o``: one string per LINE of
+    the reference's C (instructionsTableUTHash.c:1007-1029).  The emitter counts ``m`` factors per product and
+    breaks the statement once a line holds MAX_TERMS_PERLINE of them (:1019-1026), continuing with
+    ``m[d]+=...``: each line is summed left to right on its own, then added to the running value."""
+    per = -(-MAX_TERMS_PERLINE // m)            # products per line: the first count that reaches the limit
+    prods = ["*".join(o[k:k + m]) for k in range(0, len(o), m)]
+    return ["+".join(prods[k:k + per]) for k in range(0, len(prods), per)]
 
 Id = Optional[int]
 
@@ -152,6 +164,8 @@ class InstructionTable:
         self.operands: List[Tuple[int, ...]] = []
         self.names: Dict[int, str] = {}  # I_set only: debugging label
         self._index: Dict[tuple, int] = {}
+        self.sqrt_by_division = True   # see differentiate.Differentiator
+        self.split_long = True     # chunk sums of products longer than one emitted line (see MAX_TERMS_PERLINE)
 
     # -- raw access --------------------------------------------------------------
     def __len__(self) -> int:
@@ -241,7 +255,7 @@ class InstructionTable:
         if all(s > 0 and self.types[x] == I_sumprod for s, x in flat):
             ms = {self.params[x][0] for _, x in flat}
             nfac = sum(len(self.operands[x]) for _, x in flat)
-            if len(ms) == 1 and nfac <= MAX_TERMS_PERLINE:
+            if len(ms) == 1 and (nfac <= MAX_TERMS_PERLINE or not self.split_long):
                 prods: List[Tuple[int, ...]] = []
                 m = int(next(iter(ms)))
                 for _, x in flat:
@@ -258,7 +272,7 @@ class InstructionTable:
         # factors sorted inside each product, then products sorted (csparse.m:1170-1175)
         prods = sorted(tuple(sorted(p)) for p in prods)
         s = len(prods)
-        if m * s > MAX_TERMS_PERLINE:
+        if m * s > MAX_TERMS_PERLINE and self.split_long:
             # keep every emitted C statement on one line: chunk and add the chunks
             per = max(1, MAX_TERMS_PERLINE // m)
             parts = [self._sumprod(m, prods[k:k + per]) for k in range(0, s, per)]
@@ -341,7 +355,7 @@ class InstructionTable:
         ops = sorted(x for x in xs if x is not None)
         if not ops:
             return None
-        if len(ops) > MAX_TERMS_PERLINE // 2:
+        if len(ops) > MAX_TERMS_PERLINE // 2 and self.split_long:
             per = MAX_TERMS_PERLINE // 2
             return self.add([(1, self.plus_sqr(ops[k:k + per])) for k in range(0, len(ops), per)])
         return self.append_unique(I_plus_sqr, (), tuple(ops))

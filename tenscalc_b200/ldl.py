@@ -98,6 +98,23 @@ def ldl(tab: InstructionTable, A: SparseSym, order=None) -> LDLFactor:
     return LDLFactor(n, p, L, D)  # type: ignore[arg-type]
 
 
+def dense_trailing_block(F: LDLFactor) -> int:
+    """largest k such that the last k columns of the factor are completely dense -- L(r,c) structurally
+    non-zero for all n-k <= c < r < n.  A large value (box-constrained dense least squares: the whole n x n
+    Schur block once the diagonal inequality pivots are eliminated) means the scalar instruction list grows like
+    k^3/3 multiply-adds and the problem belongs on the dense kernels (``dense.py``, ``csrc/tc_dense.cu``) whose
+    trailing updates run on the FP64 tensor cores."""
+    n = F.n
+    k = 0
+    while k < n:
+        c = n - 1 - k
+        if all(c in F.L[r] for r in range(c + 1, n)):
+            k += 1
+        else:
+            break
+    return k
+
+
 def solve(tab: InstructionTable, F: LDLFactor, b: Sequence[Id]) -> List[Id]:
     """x = (P'LDL'P) \\ b  for one right-hand side given as a list of instructions."""
     n = F.n

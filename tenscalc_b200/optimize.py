@@ -181,8 +181,10 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
     problem = code.compile(defines)
     fac = info["factor"]
     from .ordering import DEFAULT as default_ordering
+    from .ldl import dense_trailing_block as ldl_dense_block
     gen_info = dict(ordering=(ordering if isinstance(ordering, str) else "custom") if ordering is not None
                     else default_ordering,
                     nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
-                    n_groups=len(problem.groups), n_slots=problem.n_slots)
+                    n_groups=len(problem.groups), n_slots=problem.n_slots,
+                    dense_block=ldl_dense_block(fac))
     return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)

@@ -153,7 +153,49 @@ def mpc_quadcopter(T_: int = 100, **opts) -> Tuple[GeneratedSolver, dict]:
     return gen, dict(mu0=1e-3, maxIter=1000)
 
 
-BUILDERS = dict(sls=sls, l1l2=l1l2, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter)
+def isa_probe(N: int = 60, **opts) -> Tuple[GeneratedSolver, dict]:
+    """Not a reference example: a small smooth bounded problem whose cost, gradient and Hessian together
+    contain every unary opcode of the scalar ISA (lib/instructionTypes.m:8-117, C forms
+    instructionsTableUTHash.c:1347-1539) and sums of products longer than one emitted line (:1019-1026,
+    ``split_long`` off), so that the parity tests execute all of them on the device against the reference's
+    own emitter.  Non-differentiable opcodes (abs, sign, round, ceil, floor, relu, heaviside) act on
+    parameters only."""
+    from .tensor import _compose, abs_, atan, cos, cube, exp, log, relu, sin, sqr, srelu
+    from . import itable as it
+    T.clear()
+    T.table().split_long = False
+    T.table().sqrt_by_division = False       # differentiate sqrt to I_Dsqrt / I_DDsqrt like the reference's table
+    n = 10
+    x = Tvariable("x", n)
+    c = Tvariable("c", n)
+    A = Tvariable("A", [N, n])
+    b = Tvariable("b", N)
+    X = [x[i] for i in range(n)]
+    C = [c[i] for i in range(n)]
+    step = (relu(C[9] - 1) + _compose(C[0] - 1, it.I_heaviside) + .1 * abs_(C[1] - 1)
+            + .1 * _compose(C[2] - 1, it.I_sign) + .1 * _compose(3 * C[3], it.I_round)
+            + .1 * _compose(3 * C[4], it.I_ceil) + .1 * _compose(3 * C[5], it.I_floor))
+    terms = [exp(X[0]) - C[0] * X[0],
+             srelu(X[1]) + sqr(X[1] - C[1]),
+             X[2] * atan(X[2]) + sqr(X[2] - C[2]),
+             C[3] * X[3] - log(X[3] + 3),
+             cube(X[4]) + 10 * sqr(X[4] - C[4]),
+             C[5] * X[5] - cos(X[5]),
+             sin(X[6]) + 2 * sqr(X[6]),
+             C[7] * X[7] - sqrt(X[7] + 3),
+             1 / (X[8] + 3) + sqr(X[8]),
+             sqr(X[9]) * (1 + step)]
+    J = norm2(A @ x - b) / N
+    for t in terms:
+        J = J + t
+    o = dict(opts)
+    gen = cmex2optimizeCS(classname="tmp_isaprobe", objective=J, optimizationVariables=[x],
+                          constraints=[x >= -1, x <= 1], outputExpressions=[J, x, step],
+                          parameters=[c, A, b], **o)
+    return gen, dict(mu0=1.0, maxIter=60)
+
+
+BUILDERS = dict(sls=sls, l1l2=l1l2, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter, isa_probe=isa_probe)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -223,6 +265,10 @@ def synthetic_inputs(name: str, gen: GeneratedSolver, batch: int, seed: int = 0)
         a[:, -1] = a[:, -2]
         u = a + b_drag * v - np.array([0, 0, 9.8])[:, None, None]
         V = dict(p=p, u=u, positive2=np.ones((T_, B)))
+    elif name == "isa_probe":
+        N, n = dict(gen.parameters)["A"]
+        P = dict(c=rng.uniform(.5, 1.5, (n, B)), A=rng.random((N, n, B)), b=rng.random((N, B)))
+        V = dict(x=.1 * rng.random((n, B)))
     else:
         raise KeyError(name)
     return P, V

@@ -47,6 +47,7 @@ ABI = [
     ("tc_set_phases", ctypes.c_int, [ctypes.c_void_p, _ip, ctypes.c_int]),
     ("tc_get_outputs", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     ("tc_get_outputs_device", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    ("tc_feedback", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _ip, _ip]),
     ("tc_synchronize", ctypes.c_int, [ctypes.c_void_p]),
     ("tc_stream", ctypes.c_void_p, [ctypes.c_void_p]),
     ("tc_last_solve_ms", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
@@ -56,6 +57,21 @@ ABI = [
     ("tc_group_counts", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     ("tc_group_warp_counts", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     ("tc_error_string", ctypes.c_char_p, [ctypes.c_int]),
+    # dense path (tenscalc_b200/dense.py)
+    ("tc_dense_create", ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    ("tc_dense_destroy", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_dense_set_A", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    ("tc_dense_set_b", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    ("tc_dense_set_x", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    ("tc_dense_solve", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p, _dp]),
+    ("tc_dense_solve_async", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp]),
+    ("tc_dense_get_outputs", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int]),
+    ("tc_dense_synchronize", ctypes.c_int, [ctypes.c_void_p]),
+    ("tc_dense_stream", ctypes.c_void_p, [ctypes.c_void_p]),
+    ("tc_dense_times_ms", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    ("tc_dense_counters", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
 ]
 
 
@@ -258,6 +274,25 @@ class BatchedSolver:
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
         fn = self._lib.tc_get_outputs_device if device else self._lib.tc_get_outputs
         _check(fn(self._h, arr))
+
+    def feedback(self, pairs: Dict[str, str]) -> None:
+        """Device-resident warm start (``tc_feedback``): ``pairs`` maps an output name to the optimisation
+        variable (or parameter) it initialises for the next solve, e.g. ``{"xWarm": "x", "uWarm": "u"}`` for
+        ``setV_x(obj,out.xWarm); setV_u(obj,out.uWarm)`` of examples/mpcmhe/mpc_dcmotor.m:223-224.  Nothing
+        crosses the host; outputs given as a list are addressed as ``y1, y2, ...``."""
+        names = [n for n, _ in self.gen.outputs]
+        oi, si = [], []
+        for o, v in pairs.items():
+            if o not in names:
+                raise TenscalcError(f"feedback: no output named {o!r}")
+            key = v if v in self._set_index else ("V_" + v if "V_" + v in self._set_index else "P_" + v)
+            if key not in self._set_index:
+                raise TenscalcError(f"feedback: no variable or parameter named {v!r}")
+            oi.append(names.index(o))
+            si.append(self._set_index[key])
+        a = (ctypes.c_int32 * max(len(oi), 1))(*oi)
+        b = (ctypes.c_int32 * max(len(si), 1))(*si)
+        _check(self._lib.tc_feedback(self._h, len(oi), a, b))
 
     def set_phased(self, on: bool = True, phases: Sequence[int] = ()) -> None:
         """phased solve on/off (csrc/tc_driver.cuh); ``phases``: iteration budget of phase 0,1,... (last repeats)"""

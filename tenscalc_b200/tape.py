@@ -130,6 +130,9 @@ def persistent_state(pr: CompiledProblem):
     return sorted(slots), static
 
 
+SELF = ("self", 0)           # operand token: the ring entry of the instruction being lowered
+
+
 def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
     """Cells [op, flags, A, B] of one instruction; ``opw`` are operand tokens in the reference's
     operand order (``None`` marks an unused operand).  The arithmetic order is that of the emitted C statement
@@ -163,6 +166,16 @@ def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
                 c.append([OP_SUM1F if k == 0 else OP_SUM1, fl, pair[0], N])
     elif t == it.I_sumprod:                                      # a*b+c*d+...         :1007-1029
         m = int(p[0])
+        per = m * -(-it.MAX_TERMS_PERLINE // m)                  # operands per emitted line (it.sumprod_lines)
+        if len(opw) > per:
+            # `m[d]=line1; m[d]+=line2; ...` (:1019-1026): every line is an accumulation of its own that ends in
+            # the instruction's ring entry; the following line adds that entry (a late operand) to its own sum
+            for k in range(0, len(opw), per):
+                c.extend(instruction_cells(t, p, opw[k:k + per]))
+                if k:
+                    c[-1][1] &= ~F_END
+                    c.append([OP_SUM1, F_END, SELF, N])
+            return c
         if m == 1:
             two(opw, OP_SUM1F, OP_SUM2F, OP_SUM1, OP_SUM2)
         elif m == 2:
@@ -260,6 +273,7 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
                 external.add(o)
 
     cells: List[List[int]] = []                 # [w0, w1, w2, w3]
+    self_ring = [0]
     group_start = [0]
     stats = dict(slot_reads=0, ring_reads=0, const_reads=0, stores=0, ring_only=0)
 
@@ -270,6 +284,8 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
         kind, v = tok
         if kind == "slot":
             return v * TILE_BYTES, 0
+        if kind == "self":
+            kind, v = "ring", self_ring[0]
         if kind == "ring":
             return (v * BLOCK * 8) | 1, late_flag
         return RING_BYTES + 8 * v, late_flag    # constant pool, stored right after the ring
@@ -305,13 +321,16 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
             cs = instruction_cells(t, p, opw)
             store = i in external or far.get(i, 0) >= ring
             stats["stores" if store else "ring_only"] += 1
+            self_ring[0] = n % ring
             for q, (op, fl, a, b_) in enumerate(cs):
                 wa, fa = enc(a, F_ALATE)
                 wb, fb = enc(b_, F_BLATE)
                 w0 = op | fl | fa | fb
                 w3 = 0
+                if fl & F_END:                  # (a multi-line sumprod ends every line in its ring entry)
+                    w0 |= (n % ring) << 16
                 if q == len(cs) - 1:
-                    w0 |= ((n % ring) << 16) | (F_STORE if store else 0)
+                    w0 |= F_STORE if store else 0
                     w3 = int(slot[i]) * TILE_BYTES if store else 0
                 cells.append([w0, wa, wb, w3])
         while len(cells) % bundle:

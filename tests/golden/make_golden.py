@@ -17,14 +17,17 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-CASES = dict(sls=24, mpc_dcmotor=24, l1l2=6, mpc_quadcopter=6)
+CASES = dict(sls=24, mpc_dcmotor=24, l1l2=6, mpc_quadcopter=6, isa_probe=24)
 SEED = 2024
 
 
 def main():
     from tenscalc_b200 import problems
     from oracle.oracle import Oracle, pack_inputs
+    only = sys.argv[1:]
     for name, B in CASES.items():
+        if only and name not in only:
+            continue
         gen, args = problems.BUILDERS[name]()
         P, V = problems.synthetic_inputs(name, gen, B, seed=SEED)
         st, it, out, _ = Oracle(gen, "ref").solve_batch(P, V, args["mu0"], args["maxIter"])

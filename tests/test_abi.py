@@ -14,7 +14,7 @@ from conftest import ROOT, generated
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "tenscalc_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(tc_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(tc_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 @pytest.fixture(scope="module")

@@ -27,6 +27,18 @@ def test_expression_forms():
     assert e(it.I_sign, [], ["x"], "r") == "const double r=(x>=0)?1.0:-1.0;"
 
 
+def test_long_sumprod_breaks_lines_like_the_reference():
+    """more than 100 factors: `m[d]=line1; m[d]+=line2;` with ceil(100/m) products per line
+    (instructionsTableUTHash.c:1019-1026) -- every line is summed on its own"""
+    o = [f"x{k}" for k in range(2 * 60)]
+    s = emit_cuda.expression(it.I_sumprod, [2, 60], o, "r")
+    first = "+".join(f"x{2 * k}*x{2 * k + 1}" for k in range(50))
+    rest = "+".join(f"x{2 * k}*x{2 * k + 1}" for k in range(50, 60))
+    assert s == f"double r={first}; r+={rest};"
+    assert len(it.sumprod_lines(3, [f"y{k}" for k in range(3 * 70)])) == 3          # 34 products per line
+    assert len(it.sumprod_lines(2, o[:100])) == 1                                    # exactly one full line
+
+
 def test_literals_are_exact():
     for v in (0.1, -2.5e-7, 1e300, 3.0, -1.0, 1 / 3):
         assert float.fromhex(emit_cuda._lit(v)) == v if "x" in emit_cuda._lit(v) else float(emit_cuda._lit(v)) == v
@@ -80,7 +92,11 @@ def test_module_builds_and_exports_entry_points():
     lib.tcm_fingerprint.restype = ctypes.c_char_p
     assert lib.tcm_fingerprint().decode() == fingerprint(gen.problem)
     assert lib.tcm_abi_version() == emit_cuda.TCM_ABI
-    assert lib.tcm_block() == 32      # one warp per CTA, one instance per lane
+    from tenscalc_b200.build import default_module_opts
+    # instances per CTA: one per lane, `lockstep` warps per CTA walk the code together (default for this size: 8)
+    assert lib.tcm_block() == 32 * default_module_opts(gen).get("lockstep", 1)
+    solo = ctypes.CDLL(build_module(gen, driver="lanes"))      # the lane-decoupled driver runs one warp per CTA
+    assert solo.tcm_block() == 32
 
 
 def test_module_path_is_content_addressed():

@@ -20,7 +20,9 @@ AFFINE = {"algorithm": "ipmPD_CS", "skipAffine": False}     # Mehrotra predictor
 CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_quadcopter", 96, {}),
          ("mpc_quadcopter", 256, {"T_": 20, "useInertia": True}),
          ("sls", 512, AFFINE), ("mpc_dcmotor", 512, AFFINE), ("mpc_dcmotor", 512, {**AFFINE, "smallerNewtonMatrix": True}),
-         ("mpc_quadcopter", 256, {"T_": 20, **AFFINE})]
+         ("mpc_quadcopter", 256, {"T_": 20, **AFFINE}),
+         # every unary opcode of the ISA (instructionsTableUTHash.c:1347-1539) and multi-line sums of products
+         ("isa_probe", 512, {})]
 
 
 def _oracle(gen, name):
@@ -216,3 +218,60 @@ def test_phased_solve_is_bit_identical_to_the_single_launch_solve(name, batch, k
     for u, v in list(zip(a[2], b[2])) + list(zip(a[3], b[3])):
         assert np.array_equal(u, v, equal_nan=True)
     assert len(np.unique(a[1])) > 1          # instances really finish at different iterations
+
+
+def test_receding_horizon_warm_start_stays_on_device():
+    """The MPC loop of examples/mpcmhe/mpc_dcmotor.m:192-225 -- solve, apply u(:,1) to the plant, shift the
+    reference, warm-start the next solve with out.xWarm/out.uWarm -- with the warm start fed back ON THE DEVICE
+    (tc_feedback) against the oracle run through host arrays like the reference script: identical status,
+    iterations and outputs at every step of the closed loop."""
+    from oracle.oracle import Oracle
+    name, B, steps = "mpc_dcmotor", 256, 6
+    gen, args = generated(name)
+    P, V = problems.synthetic_inputs(name, gen, B, seed=11)
+    P = {k: np.array(v, dtype=float) for k, v in P.items()}
+    Ts, p, k = .1, -2., 1.
+    # exact zero-order-hold discretisation of xdot=[0 1;0 p]x+[0;k]u
+    e = np.exp(p * Ts)
+    Ad = np.array([[1, (e - 1) / p], [0, e]])
+    Bd = np.array([k * ((e - 1) / p - Ts) / p, k * (e - 1) / p])
+    T_ = P["ref"].shape[1]
+    t0 = np.random.default_rng(3).uniform(0, 4 * np.pi, B)
+    oracle = Oracle(gen, "ref")
+    obj = gen(B)
+    for n, _ in gen.parameters:
+        getattr(obj, "setP_" + n)(P[n])
+    for n, _ in gen.variables:
+        getattr(obj, "setV_" + n)(V[n])
+    Vk = dict(V)
+    warm_iters, cold_iters = 0, 0
+    for step in range(steps):
+        st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+        out = obj.getOutputs()
+        st_o, it_o, out_o, _ = oracle.solve_batch(P, Vk, args["mu0"], args["maxIter"])
+        assert np.array_equal(st, st_o), step
+        assert np.array_equal(it, it_o), step
+        for key in out_o:
+            assert np.array_equal(out[key], out_o[key]), (step, key)
+        cold_iters += int(it.sum()) if step == 0 else 0
+        warm_iters += int(it.sum()) if step == steps - 1 else 0
+        # device: warm start without a host round trip; host oracle: the reference script's arrays
+        obj.feedback({"xWarm": "x", "uWarm": "u"})
+        Vk = dict(x=out_o["xWarm"], u=out_o["uWarm"])
+        xinit = P["xinit"][:, 0, :]
+        xinit = Ad @ xinit + Bd[:, None] * out_o["u"][0, 0, :][None, :]
+        tt = t0[None, :] + Ts * (step + 1 + np.arange(T_))[:, None]
+        P["xinit"] = xinit[:, None, :]
+        P["ref"] = (-.35 * np.sign(np.sin(.5 * tt)))[None, :, :]
+        obj.setP_xinit(P["xinit"])
+        obj.setP_ref(P["ref"])
+    obj.close()
+    print(f"closed loop {steps} steps x {B} instances: {cold_iters / B:.1f} iterations cold, {warm_iters / B:.1f} warm")
+
+
+def test_feedback_rejects_mismatched_sizes():
+    gen, _ = generated("mpc_dcmotor")
+    obj = gen(64)
+    with pytest.raises(Exception):
+        obj.feedback({"J": "x"})
+    obj.close()

@@ -19,7 +19,8 @@ from conftest import ROOT, generated
 from tenscalc_b200 import problems
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-NAMES = ["sls", "mpc_dcmotor", "l1l2", "mpc_quadcopter"]
+# isa_probe: every unary opcode + sums of products longer than one emitted line (problems.isa_probe)
+NAMES = ["sls", "mpc_dcmotor", "l1l2", "mpc_quadcopter", "isa_probe"]
 
 
 def _load(name):
@@ -145,21 +146,24 @@ def test_port_emitter_text_equals_reference_emitter():
         pytest.skip("reference emitter not available")
     from oracle.build_ref import build_itable
     build_itable()
-    gen, _ = generated("sls")
-    pr = gen.problem
-    ref = emit_c.RefEmitter(pr)
-
     def norm(txt):
         txt = re.sub(r"//[^\n]*", "", txt)
         return re.sub(r"\s+", "", txt)
-    checked = 0
-    for members in pr.groups:
-        a = norm(ref.statements(members, min4loop=10 ** 9))
-        b = norm("".join(emit_c.statement(pr.tab, i, pr.slot) for i in members))
-        # the reference prints constants with %.20e as well; clp temporaries are named the same
-        assert a == b
-        checked += len(members)
-    assert checked > 500
+    # isa_probe: all unary opcodes and the `m[d]=...; m[d]+=...;` line breaks of long sums of products
+    for name in ("sls", "isa_probe"):
+        gen, _ = generated(name)
+        pr = gen.problem
+        ref = emit_c.RefEmitter(pr)
+        checked = 0
+        for members in pr.groups:
+            a = norm(ref.statements(members, min4loop=10 ** 9))
+            b = norm("".join(emit_c.statement(pr.tab, i, pr.slot) for i in members))
+            # the reference prints constants with %.20e as well; clp temporaries are named the same
+            assert a == b, name
+            checked += len(members)
+        assert checked > 500
+        if name == "isa_probe":
+            assert "]+=" in a or any("]+=" in norm(ref.statements(m, min4loop=10 ** 9)) for m in pr.groups)
 
 
 def test_inertia_controlled_regularisation_port_equals_reference():
