@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mpc_quadcopter", choices=sorted(DEFAULT_BATCH))
+    ap.add_argument("--workload", default="mpc_quadcopter", choices=sorted(DEFAULT_BATCH) + ["dense_ls"])
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the BASELINE batch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per core in the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -613,7 +613,13 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.impl == "reference":
+    if args.workload == "dense_ls":        # BASELINE config 5 runs on the dense path (bench_dense.py)
+        import bench_dense
+        if args.impl == "reference":
+            bench_dense.run_reference(args, rank, METRIC, UNIT)
+        else:
+            bench_dense.run_ours(args, rank, local_rank, world, METRIC, UNIT, ClockSampler)
+    elif args.impl == "reference":
         run_reference(args, rank)
     else:
         run_ours(args, rank, local_rank, world)

@@ -11,6 +11,10 @@ CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}
            ("mpc_quadcopter", {"T_": 20, "useInertia": True}),    # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
            ("sls", AFFINE), ("mpc_dcmotor", AFFINE), ("mpc_dcmotor", AFFINE_SMALL),
            ("mpc_quadcopter", {"T_": 20, **AFFINE})]
+# ipmPDeq_CSsolver (equilibria): the reference's own driver is the only oracle (kind "ref")
+EQ_CONFIGS = [("matrix_game", {}), ("qsaddle", {}), ("qsaddle_latent", {}), ("qsaddle", {"useLDL": True}),
+              ("matrix_game", {"skipAffine": False}),
+              ("qsaddle", {"addEye2Hessian": True, "adjustAddEye2Hessian": True})]   # regulariser control of the eq driver (:318-374)
 
 
 # extra builds of the benchmark workload: the toolbox's default -O0 and -O2 beside the headline -O1
@@ -38,6 +42,8 @@ def build_all(kinds=("ref", "port"), configs=CONFIGS, workers=4, extra=True):
         for k in kinds:
             print("oracle dense_ls", N, n, k, DenseOracle(N, n, lo, hi, k).build())
     jobs = [(n, kw, k, "-O1", "") for n, kw in configs for k in kinds]
+    if "ref" in kinds:
+        jobs += [(n, kw, "ref", "-O1", "") for n, kw in EQ_CONFIGS]
     if extra:
         jobs += [(n, kw, kinds[0], opt, var) for n, kw, opt, var in EXTRA]
     with ProcessPoolExecutor(workers) as ex:

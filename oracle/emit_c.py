@@ -41,7 +41,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 MAX_PER_FUNCTION = 200
 
-_DOUBLE_DEFINES = ("gradTolerance", "addEye2HessianUtolerance", "equalTolerance", "desiredDualityGap",
+_DOUBLE_DEFINES = ("gradTolerance", "addEye2HessianUtolerance", "addEye2Hessian1tolerance", "equalTolerance", "desiredDualityGap",
                    "alphaMin", "alphaMax", "muFactorAggressive", "muFactorConservative")
 
 
@@ -196,8 +196,10 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
       "  if (y==-1.5 && x>1e-190 && x<1e190){oracle_rsqrt_dd(x,&h,&l); double q0=h/x,rem=fma(-q0,x,h); return q0+(rem+l)/x;}\n"
       "  return pow(x,y);}\n"
       "#define pow(x,y) oracle_crpow(x,y)\n#endif\n")
+    solver = str(pr.defines.get("driver", "ipmPD_CSsolver"))       # which of the reference's drivers the class calls
     for k, v in pr.defines.items():
-        w(f"#define {k} {v:e}\n" if k in _DOUBLE_DEFINES else f"#define {k} {v}\n")
+        if k != "driver":
+            w(f"#define {k} {v:e}\n" if k in _DOUBLE_DEFINES else f"#define {k} {v}\n")
     w(f"static SCRATCHBOOK_TYPE scratchbook[{max(pr.n_slots, 1)}];\n")
     w(f"static int groupStatus[{max(len(pr.groups), 1)}];\n")
     for g, members in enumerate(pr.groups):
@@ -230,7 +232,9 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
             w(f"static void {name}({sig}) {{ *mp=0; *mn=0; }}\n")
 
     if driver == "ref":
-        w('#include "/root/reference/lib/ipmPD_CSsolver.c"\n')
+        w(f'#include "/root/reference/lib/{solver}.c"\n')
+    elif solver != "ipmPD_CSsolver":
+        raise NotImplementedError(f"{solver}: only the reference's own driver is used as oracle (kind='ref')")
     else:
         w(f'#include "{os.path.join(HERE, "ipm_driver_port.c")}"\n')
 
@@ -253,7 +257,7 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
         w(f"    {f}(v+{off});\n")
         off += n
     w("    struct timespec t0,t1; clock_gettime(CLOCK_MONOTONIC,&t0);\n")
-    w("    ipmPD_CSsolver(&mu,&mi,&si,ae,status+b,iter+b,&t);\n")
+    w(f"    status[b]=0; {solver}(&mu,&mi,&si,ae,status+b,iter+b,&t);\n")
     w("    clock_gettime(CLOCK_MONOTONIC,&t1);\n")
     w("    if (seconds) seconds[b]=(t1.tv_sec-t0.tv_sec)+1e-9*(t1.tv_nsec-t0.tv_nsec);\n")
     offs = np.concatenate([[0], np.cumsum(nout)])

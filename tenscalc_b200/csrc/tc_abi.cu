@@ -394,6 +394,8 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     D.scaleCost = (int32_t)ih[19]; D.scaleInequalities = (int32_t)ih[20]; D.coupledAlphas = (int32_t)ih[21];
     D.setAddEye2Hessian = (int32_t)ih[22]; D.adjustAddEye2Hessian = (int32_t)ih[23];
     D.useInertia = (int32_t)ih[24]; D.skipAffine = (int32_t)ih[25]; D.delta = (int32_t)ih[26];
+    D.driver = (int32_t)ih[27];
+    if (D.driver != 0 && D.driver != 1) { tc_destroy(s); return TC_EFORMAT; }
     D.gradTolerance = dh[0]; D.addEye2HessianUtolerance = dh[1]; D.equalTolerance = dh[2];
     D.desiredDualityGap = dh[3]; D.alphaMin = dh[4]; D.alphaMax = dh[5];
     D.muFactorAggressive = dh[6]; D.muFactorConservative = dh[7];

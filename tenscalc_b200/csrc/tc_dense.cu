@@ -32,9 +32,14 @@
 #include "../../include/tenscalc_b200.h"
 
 #define TCD_THREADS 256
-#define TCD_NB 32            // panel width of the blocked LDL'
-#define TCD_LDS 36           // row stride (doubles) of the panel buffers: = 4 mod 16 -> conflict-free DMMA fragment loads
+#define TCD_NB 16            // panel width of the blocked LDL' (the serial work per factorisation grows with it)
+#define TCD_LDS 20           // row stride (doubles) of the panel buffers: = 4 mod 16 -> conflict-free DMMA fragment loads
+#ifndef TCD_CTAS
+#define TCD_CTAS 2           // resident CTAs per SM of the solve kernel (register budget 65536/(256*TCD_CTAS))
+#endif
+#define TCD_SB 32            // block width of the triangular solves (one warp per diagonal block)
 #define TCD_KC 32            // rows of A per shared-memory stage of the Gram kernel
+#define TCD_GLDS 36          // row stride (doubles) of a Gram stage, = 4 mod 16
 
 #define TCD_CUDA(x)                             \
     do {                                        \
@@ -56,16 +61,24 @@ __device__ __forceinline__ void tcd_dmma(double &c0, double &c1, double a, doubl
 // stages of TCD_KC rows through shared memory, stored transposed [column][k] so that the global reads (a column's
 // 32 consecutive rows = 256 B) and the fragment loads are both conflict-free.
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tcd_cp_async8(double *smem_dst, const double *gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 8 : 0;               // src-size 0: the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
 template <int NT>   // NT = n/8 tile columns
 __global__ void __launch_bounds__(TCD_THREADS) tcd_gram_kernel(const double *__restrict__ A, const double *__restrict__ b,
                                                               int64_t N, double *__restrict__ H0,
                                                               double *__restrict__ g0, double *__restrict__ c0) {
     constexpr int n = NT * 8;
-    extern __shared__ double sm[];                 // [(n + 8)][TCD_LDS]
+    constexpr int STAGE = (n + 8) * TCD_GLDS;       // doubles per shared-memory stage
+    extern __shared__ double sm[];                 // [2][(n + 8)][TCD_GLDS]
     const int64_t inst = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tr = blockIdx.y * 8 + warp;          // tile row of this warp
     const int tc0 = blockIdx.y * 8;                // first tile column of the block (upper triangle by blocks)
+    const int j0 = tc0 * 8;                        // only the columns >= j0 are needed by this block
     const double *Ai = A + (size_t)inst * (size_t)N * n;
     const double *bi = b + (size_t)inst * (size_t)N;
     double acc[NT + 1][2];
@@ -73,33 +86,42 @@ __global__ void __launch_bounds__(TCD_THREADS) tcd_gram_kernel(const double *__r
     for (int t = 0; t <= NT; t++) acc[t][0] = acc[t][1] = 0.0;
     double bsq = 0.0;
     const bool active = tr < NT;
-    for (int64_t k0 = 0; k0 < N; k0 += TCD_KC) {
-        __syncthreads();
-        // stage: column j of A rows k0..k0+31 -> sm[j][0..31]; column n = b, columns n+1..n+7 = 0
-        for (int j = warp; j < n + 8; j += TCD_THREADS / 32) {
-            const int64_t k = k0 + lane;
-            double v = 0.0;
-            if (k < N) {
-                if (j < n) v = Ai[k + (size_t)N * j];
-                else if (j == n) v = bi[k];
-            }
-            sm[j * TCD_LDS + lane] = v;
+    for (int e = threadIdx.x; e < 2 * 7 * TCD_GLDS; e += TCD_THREADS)          // zero padding of the b tile, both stages
+        sm[(e / (7 * TCD_GLDS)) * STAGE + (n + 1) * TCD_GLDS + e % (7 * TCD_GLDS)] = 0.0;
+    // cp.async double buffering: stage s+1 (rows k0+32.. of the needed columns, 256 contiguous bytes per warp and
+    // column, written transposed [column][k]) is in flight while the tensor cores work on stage s
+    auto issue = [&](int64_t k0, int buf) {
+        const int64_t k = k0 + lane;
+        for (int j = j0 + warp; j <= n; j += TCD_THREADS / 32)
+            tcd_cp_async8(sm + buf * STAGE + j * TCD_GLDS + lane, j < n ? Ai + k + (size_t)N * j : bi + k, k < N);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0, 0);
+    int buf = 0;
+    for (int64_t k0 = 0; k0 < N; k0 += TCD_KC, buf ^= 1) {
+        if (k0 + TCD_KC < N) {
+            issue(k0 + TCD_KC, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        __syncthreads();
-        if (blockIdx.y == 0 && warp == 0) { const double v = sm[n * TCD_LDS + lane]; bsq += v * v; }
+        __syncthreads();                           // stage `buf` is complete and visible
+        const double *st = sm + buf * STAGE;
+        if (blockIdx.y == 0 && warp == 0) { const double v = st[n * TCD_GLDS + lane]; bsq += v * v; }
         if (active) {
 #pragma unroll
             for (int kk = 0; kk < TCD_KC / 4; kk++) {
-                const double a = sm[(tr * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)];
+                const double a = st[(tr * 8 + (lane >> 2)) * TCD_GLDS + 4 * kk + (lane & 3)];
 #pragma unroll
                 for (int t = 0; t <= NT; t++) {
                     if (t >= tc0) {            // uniform per CTA
-                        const double bf = sm[(t * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)];
+                        const double bf = st[(t * 8 + (lane >> 2)) * TCD_GLDS + 4 * kk + (lane & 3)];
                         tcd_dmma(acc[t][0], acc[t][1], a, bf);
                     }
                 }
             }
         }
+        __syncthreads();                           // everybody is done with `buf` before the next issue overwrites it
     }
     const double scale = 2.0 / (double)N;
     if (active) {
@@ -149,9 +171,9 @@ struct tcd_smem {
     double red[TCD_THREADS / 32];
     double vec[TCD_THREADS];      // vector operand of the matrix-vector products / right-hand side of the solves
     double diag[TCD_NB * (TCD_NB + 1)];
-    double dd[TCD_NB], vrow[TCD_NB];
+    double dd[TCD_NB], rd[TCD_NB];             // D of the current diagonal block and 1/D
     double Ls[(TCD_THREADS - 8) * TCD_LDS];   // L21 of the current panel, [row][TCD_LDS]
-    double Ws[(TCD_THREADS - 8) * TCD_LDS];   // L21 * D
+    double dW[TCD_NB];                        // -D of that panel (the A operand of its trailing update is L21 * -D)
 };
 
 enum { RED_SUM = 0, RED_MIN, RED_MAX };
@@ -183,14 +205,59 @@ __device__ __forceinline__ double tcd_matvec(const double *__restrict__ M, int n
     __syncthreads();
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     if (i < n) {
-        for (int j = 0; j < n; j += 4) {
-            a0 += M[i + (size_t)n * j] * S.vec[j];
-            a1 += M[i + (size_t)n * (j + 1)] * S.vec[j + 1];
-            a2 += M[i + (size_t)n * (j + 2)] * S.vec[j + 2];
-            a3 += M[i + (size_t)n * (j + 3)] * S.vec[j + 3];
+#pragma unroll 2
+        for (int j = 0; j < n; j += 8) {           // n is a multiple of 8; eight loads in flight per thread
+            const double m0 = M[i + (size_t)n * j], m1 = M[i + (size_t)n * (j + 1)], m2 = M[i + (size_t)n * (j + 2)],
+                         m3 = M[i + (size_t)n * (j + 3)], m4 = M[i + (size_t)n * (j + 4)], m5 = M[i + (size_t)n * (j + 5)],
+                         m6 = M[i + (size_t)n * (j + 6)], m7 = M[i + (size_t)n * (j + 7)];
+            a0 = fma(m0, S.vec[j], a0); a1 = fma(m1, S.vec[j + 1], a1); a2 = fma(m2, S.vec[j + 2], a2); a3 = fma(m3, S.vec[j + 3], a3);
+            a0 = fma(m4, S.vec[j + 4], a0); a1 = fma(m5, S.vec[j + 5], a1); a2 = fma(m6, S.vec[j + 6], a2); a3 = fma(m7, S.vec[j + 7], a3);
         }
     }
     return (a0 + a1) + (a2 + a3);
+}
+
+// Tiles (ti, tj), tj0 <= tj <= min(ti, tj1-1), of the trailing update A22 -= (L21 D) L21' of one panel: 8x8 DMMA tiles.
+// The warps `wid` of `nw` take whole tile rows (long and short rows alternate, so every warp gets about the same
+// number of tiles), keep the row's A fragments in registers and walk the row four tiles at a time with the loads of
+// the C tiles issued first.
+__device__ __forceinline__ void tcd_trailing(double *__restrict__ W22, int n, int mt, int tj0, int tj1, int wid, int nw,
+                                             const tcd_smem &S, unsigned long long &flops) {
+    const int lane = threadIdx.x & 31;
+    const int rows = mt - tj0;                                    // tile rows tj0 .. mt-1 have tiles in the range
+    for (int q = wid; q < rows; q += nw) {
+        const int ti = tj0 + ((q & 1) ? (q >> 1) : (rows - 1 - (q >> 1)));
+        const int tend = min(ti + 1, tj1);
+        double af[TCD_NB / 4];
+#pragma unroll
+        for (int kk = 0; kk < TCD_NB / 4; kk++)
+            af[kk] = S.Ls[(ti * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)] * S.dW[4 * kk + (lane & 3)];
+        const int r = ti * 8 + (lane >> 2);
+        for (int t0 = tj0; t0 < tend; t0 += 4) {
+            double c0[4], c1[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (t0 + u < tend) {
+                    const int c = (t0 + u) * 8 + 2 * (lane & 3);
+                    c0[u] = W22[r + (size_t)n * c];
+                    c1[u] = W22[r + (size_t)n * (c + 1)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (t0 + u < tend) {
+                    const int tj = t0 + u;
+#pragma unroll
+                    for (int kk = 0; kk < TCD_NB / 4; kk++)
+                        tcd_dmma(c0[u], c1[u], af[kk], S.Ls[(tj * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)]);
+                    const int c = tj * 8 + 2 * (lane & 3);
+                    W22[r + (size_t)n * c] = c0[u];
+                    W22[r + (size_t)n * (c + 1)] = c1[u];
+                    if (lane == 0) flops += 2ull * 8 * 8 * TCD_NB;
+                }
+            }
+        }
+    }
 }
 
 // Blocked right-looking LDL' of the symmetric matrix whose LOWER triangle is in W (n x n, column-major), in place:
@@ -198,42 +265,68 @@ __device__ __forceinline__ double tcd_matvec(const double *__restrict__ M, int n
 // rows of L' with consecutive threads on consecutive addresses).  Recipe per column as sparsity_ldl.m:144-236
 // (v_i = L(col,i) D(i), D(col) = A(col,col) - sum L(col,i) v_i, L(row,col) = (A(row,col) - sum L(row,i) v_i)/D(col),
 // no pivoting); the trailing update A22 -= (L21 D) L21' runs on the FP64 tensor cores.
-__device__ void tcd_ldl(double *__restrict__ W, int n, tcd_smem &S, unsigned long long &flops) {
+// Look-ahead: of a panel's trailing update only the tiles in the NEXT panel's columns are applied at once; the rest
+// is applied by warps 1..7 while warp 0 runs the (serial) factorisation of the next diagonal block.
+__device__ __noinline__ void tcd_ldl(double *__restrict__ W, int n, tcd_smem &S, unsigned long long &flops) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int prev_mt = 0;                       // tile rows of the previous panel's trailing matrix (0: nothing pending)
+    double *prev_W22 = W;
     for (int k0 = 0; k0 < n; k0 += TCD_NB) {
         const int nb = min(TCD_NB, n - k0), m = n - k0 - nb;
         __syncthreads();
         for (int e = tid; e < nb * nb; e += TCD_THREADS) {             // diagonal block -> shared memory
             const int r = e % nb, c = e / nb;
-            S.diag[r * (TCD_NB + 1) + c] = W[(k0 + r) + (size_t)n * (k0 + c)];
+            if (c <= r) S.diag[r * (TCD_NB + 1) + c] = W[(k0 + r) + (size_t)n * (k0 + c)];
         }
         __syncthreads();
-        if (warp == 0) {                                                // unblocked LDL' of the nb x nb block
+        if (warp == 0) {
+            // right-looking elimination of the nb x nb block in shared memory: lane r owns row r; column j, which
+            // every lane needs at step j, is a broadcast read
             for (int j = 0; j < nb; j++) {
-                if (lane < j) S.vrow[lane] = S.diag[j * (TCD_NB + 1) + lane] * S.dd[lane];
+                const double dj = S.diag[j * (TCD_NB + 1) + j];        // D(j): row j is final
+                const double rj = 1.0 / dj;                             // one reciprocal per column; L = A * (1/D)
+                double l = 0.0;
+                if (lane > j && lane < nb) {
+                    l = S.diag[lane * (TCD_NB + 1) + j] * rj;           // L(r,j)
+                    S.diag[lane * (TCD_NB + 1) + j] = l;
+                }
+                if (lane == j) S.rd[j] = rj;
                 __syncwarp();
-                double acc = 0.0;
-                if (lane >= j && lane < nb)
-                    for (int i = 0; i < j; i++) acc += S.diag[lane * (TCD_NB + 1) + i] * S.vrow[i];
-                if (lane == j) S.dd[j] = S.diag[j * (TCD_NB + 1) + j] - acc;
-                __syncwarp();
-                if (lane > j && lane < nb)
-                    S.diag[lane * (TCD_NB + 1) + j] = (S.diag[lane * (TCD_NB + 1) + j] - acc) / S.dd[j];
+                if (lane > j && lane < nb) {
+                    const double vr = -(l * dj);                        // -v_j = -L(r,j) D(j)
+                    double *row = S.diag + lane * (TCD_NB + 1);
+                    int c = j + 1;
+                    for (; c + 3 <= lane; c += 4) {                     // A(r,c) -= L(r,j) D(j) L(c,j), four at a time
+                        const double l0 = S.diag[c * (TCD_NB + 1) + j], l1 = S.diag[(c + 1) * (TCD_NB + 1) + j],
+                                     l2 = S.diag[(c + 2) * (TCD_NB + 1) + j], l3 = S.diag[(c + 3) * (TCD_NB + 1) + j];
+                        const double r0 = row[c], r1 = row[c + 1], r2 = row[c + 2], r3 = row[c + 3];
+                        row[c] = fma(vr, l0, r0); row[c + 1] = fma(vr, l1, r1); row[c + 2] = fma(vr, l2, r2); row[c + 3] = fma(vr, l3, r3);
+                    }
+                    for (; c <= lane; c++) row[c] = fma(vr, S.diag[c * (TCD_NB + 1) + j], row[c]);
+                }
                 __syncwarp();
             }
+            if (lane < nb) S.dd[lane] = S.diag[lane * (TCD_NB + 1) + lane];
+        } else if (prev_mt > TCD_NB / 8) {
+            // meanwhile: the previous panel's trailing tiles outside the current panel's columns
+            tcd_trailing(prev_W22, n, prev_mt, TCD_NB / 8, prev_mt, warp - 1, TCD_THREADS / 32 - 1, S, flops);
         }
         __syncthreads();
-        for (int e = tid; e < nb * nb; e += TCD_THREADS) {             // write the factored block back (+ mirror)
+        for (int e = tid; e < nb * nb; e += TCD_THREADS) {             // factor -> W (+ mirror); V = L D -> S.diag
             const int r = e % nb, c = e / nb;
             if (r == c) W[(k0 + r) + (size_t)n * (k0 + c)] = S.dd[r];
             else if (r > c) {
                 const double l = S.diag[r * (TCD_NB + 1) + c];
                 W[(k0 + r) + (size_t)n * (k0 + c)] = l;
                 W[(k0 + c) + (size_t)n * (k0 + r)] = l;
+                S.diag[r * (TCD_NB + 1) + c] = l * S.dd[c];
             }
         }
+        __syncthreads();
+        prev_mt = 0;
         if (m == 0) break;
-        // panel: one thread per row below the block; the row stays in registers
+        // ---- panel: one thread per row below the block; the row stays in registers (right-looking: the updates of
+        // one step are independent of each other) ----
         if (tid < m) {
             const int row = k0 + nb + tid;
             double a[TCD_NB];
@@ -242,90 +335,91 @@ __device__ void tcd_ldl(double *__restrict__ W, int n, tcd_smem &S, unsigned lon
 #pragma unroll
             for (int j = 0; j < TCD_NB; j++) {
                 if (j < nb) {
-                    double acc = 0.0;
+                    const double l = a[j] * S.rd[j];                    // L(row,j) = A(row,j) * (1/D(j))
+                    a[j] = l;
 #pragma unroll
-                    for (int i = 0; i < TCD_NB; i++)
-                        if (i < j) acc += a[i] * (S.diag[j * (TCD_NB + 1) + i] * S.dd[i]);
-                    a[j] = (a[j] - acc) / S.dd[j];
+                    for (int c = j + 1; c < TCD_NB; c++)
+                        if (c < nb) a[c] = fma(-l, S.diag[c * (TCD_NB + 1) + j], a[c]);   // A(row,c) -= L(row,j) (L(c,j) D(j))
                 }
             }
 #pragma unroll
             for (int j = 0; j < TCD_NB; j++) {
                 const double l = j < nb ? a[j] : 0.0;
                 S.Ls[tid * TCD_LDS + j] = l;
-                S.Ws[tid * TCD_LDS + j] = j < nb ? -(l * S.dd[j]) : 0.0;     // minus: the update is a subtraction
                 if (j < nb) {
                     W[row + (size_t)n * (k0 + j)] = l;
                     W[(k0 + j) + (size_t)n * row] = l;
                 }
             }
         }
+        if (tid < TCD_NB) S.dW[tid] = tid < nb ? -S.dd[tid] : 0.0;       // minus: the update is a subtraction
         __syncthreads();
-        // trailing update of the lower triangle, 8x8 tiles round-robin over the warps
-        const int mt = m / 8, ntiles = mt * (mt + 1) / 2;
-        double *W22 = W + (size_t)(k0 + nb) * n + (k0 + nb);
-        for (int t = warp; t < ntiles; t += TCD_THREADS / 32) {
-            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);   // tile row: ti(ti+1)/2 <= t
-            while (ti * (ti + 1) / 2 > t) ti--;
-            while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-            const int tj = t - ti * (ti + 1) / 2;
-            const int r = ti * 8 + (lane >> 2), c = tj * 8 + 2 * (lane & 3);
-            double c0 = W22[r + (size_t)n * c], c1 = W22[r + (size_t)n * (c + 1)];
-#pragma unroll
-            for (int kk = 0; kk < TCD_NB / 4; kk++) {
-                const double af = S.Ws[(ti * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)];
-                const double bf = S.Ls[(tj * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)];
-                tcd_dmma(c0, c1, af, bf);
-            }
-            W22[r + (size_t)n * c] = c0;
-            W22[r + (size_t)n * (c + 1)] = c1;
-            if (lane == 0) flops += 2ull * 8 * 8 * TCD_NB;
-        }
+        // ---- trailing update, urgent part: the tiles in the next panel's columns (all warps) ----
+        prev_mt = m / 8;
+        prev_W22 = W + (size_t)(k0 + nb) * n + (k0 + nb);
+        tcd_trailing(prev_W22, n, prev_mt, 0, TCD_NB / 8, warp, TCD_THREADS / 32, S, flops);
     }
     __syncthreads();
 }
 
 // x = (L D L') \ b with the factor of tcd_ldl; thread i holds b_i and receives x_i
-__device__ double tcd_ldl_solve(const double *__restrict__ W, int n, double bi, tcd_smem &S) {
-    const int i = threadIdx.x;
-    // forward substitution, panel by panel: warp 0 solves the nb x nb unit-lower block with shuffles, then every
-    // row below subtracts the panel's contribution
+__device__ __noinline__ double tcd_ldl_solve(const double *__restrict__ W, int n, double bi, tcd_smem &S) {
+    const int i = threadIdx.x, lane = i & 31;
+    // forward substitution, panel by panel: the warp that owns the panel solves the nb x nb unit-lower block with
+    // shuffles (its rows of the block are loaded into registers first: no memory access inside the dependent
+    // chain), then every row below subtracts the panel's contribution
     double y = bi;
-    for (int k0 = 0; k0 < n; k0 += TCD_NB) {
-        const int nb = min(TCD_NB, n - k0);
-        const unsigned mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        if (i >= k0 && i < k0 + nb) {                       // one warp (k0 is a multiple of 32)
-            for (int j = 0; j < nb; j++) {
-                const double yj = __shfl_sync(mask, y, j);
-                if (i - k0 > j) y -= W[i + (size_t)n * (k0 + j)] * yj;
+    for (int k0 = 0; k0 < n; k0 += TCD_SB) {
+        const int nb = min(TCD_SB, n - k0);
+        if (i >= k0 && i < k0 + TCD_SB) {                   // one whole warp (k0 is a multiple of 32)
+            double lrow[TCD_SB];
+#pragma unroll
+            for (int j = 0; j < TCD_SB; j++) lrow[j] = (j < lane && lane < nb) ? W[i + (size_t)n * (k0 + j)] : 0.0;
+#pragma unroll
+            for (int j = 0; j < TCD_SB; j++) {
+                const double yj = __shfl_sync(0xffffffffu, y, j);
+                y -= lrow[j] * yj;                          // lrow[j] = 0 for j >= lane
             }
-            S.vec[i] = y;
+            if (lane < nb) S.vec[i] = y;
         }
         __syncthreads();
         if (i >= k0 + nb && i < n) {
-            double acc = 0.0;
-            for (int j = 0; j < nb; j++) acc += W[i + (size_t)n * (k0 + j)] * S.vec[k0 + j];
-            y -= acc;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int j = 0; j < nb; j += 4) {
+                a0 += W[i + (size_t)n * (k0 + j)] * S.vec[k0 + j];
+                a1 += W[i + (size_t)n * (k0 + j + 1)] * S.vec[k0 + j + 1];
+                a2 += W[i + (size_t)n * (k0 + j + 2)] * S.vec[k0 + j + 2];
+                a3 += W[i + (size_t)n * (k0 + j + 3)] * S.vec[k0 + j + 3];
+            }
+            y -= (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
     }
     if (i < n) y = y / W[i + (size_t)n * i];
     // backward substitution with L' (mirrored into the upper triangle), last panel first
-    for (int k0 = ((n - 1) / TCD_NB) * TCD_NB; k0 >= 0; k0 -= TCD_NB) {
-        const int nb = min(TCD_NB, n - k0);
-        const unsigned mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        if (i >= k0 && i < k0 + nb) {
-            for (int j = nb - 1; j >= 0; j--) {
-                const double xj = __shfl_sync(mask, y, j);
-                if (i - k0 < j) y -= W[i + (size_t)n * (k0 + j)] * xj;
+    for (int k0 = ((n - 1) / TCD_SB) * TCD_SB; k0 >= 0; k0 -= TCD_SB) {
+        const int nb = min(TCD_SB, n - k0);
+        if (i >= k0 && i < k0 + TCD_SB) {
+            double lrow[TCD_SB];
+#pragma unroll
+            for (int j = 0; j < TCD_SB; j++) lrow[j] = (j > lane && j < nb) ? W[i + (size_t)n * (k0 + j)] : 0.0;
+#pragma unroll
+            for (int j = TCD_SB - 1; j >= 0; j--) {
+                const double xj = __shfl_sync(0xffffffffu, y, j);
+                y -= lrow[j] * xj;                          // lrow[j] = 0 for j <= lane
             }
-            S.vec[i] = y;
+            if (lane < nb) S.vec[i] = y;
         }
         __syncthreads();
         if (i < k0) {
-            double acc = 0.0;
-            for (int j = 0; j < nb; j++) acc += W[i + (size_t)n * (k0 + j)] * S.vec[k0 + j];
-            y -= acc;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int j = 0; j < nb; j += 4) {
+                a0 += W[i + (size_t)n * (k0 + j)] * S.vec[k0 + j];
+                a1 += W[i + (size_t)n * (k0 + j + 1)] * S.vec[k0 + j + 1];
+                a2 += W[i + (size_t)n * (k0 + j + 2)] * S.vec[k0 + j + 2];
+                a3 += W[i + (size_t)n * (k0 + j + 3)] * S.vec[k0 + j + 3];
+            }
+            y -= (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
     }
@@ -338,7 +432,7 @@ __device__ double tcd_ldl_solve(const double *__restrict__ W, int n, double bi, 
 // ipmPD_CSsolver() (lib/ipmPD_CSsolver.c:132-920) for the option set cmex2optimizeCS generates for this problem
 // (nG=0, nF=2n, skipAffine=1, adjustAddEye2Hessian=1, useInertia=0, scaleCost=0, scaleInequalities=1,
 // coupledAlphas=1), one instance per CTA; CTAs take instances from the grid-strided range.
-__global__ void __launch_bounds__(TCD_THREADS, 1) tcd_solve_kernel(tcd_args P) {
+__global__ void __launch_bounds__(TCD_THREADS, TCD_CTAS) tcd_solve_kernel(tcd_args P) {
     extern __shared__ double smraw[];
     tcd_smem &S = *reinterpret_cast<tcd_smem *>(smraw);
     const int n = P.n, i = threadIdx.x;
@@ -370,13 +464,21 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) tcd_solve_kernel(tcd_args P) {
             const double DF1 = -(F1 * l1), DF2 = -(F2 * l2);
             const double LF1 = (-(l1 * s1)) / DF1, LF2 = (l2 * s2) / DF2;
             __syncthreads();
-            for (int j = 0; j < n; j++)                                         // W = H0 (coalesced copy)
-                if (on) W[i + (size_t)n * j] = H0[i + (size_t)n * j];
+            if (on) {                                                           // W = H0 (coalesced copy, 8 loads in flight)
+#pragma unroll 2
+                for (int j = 0; j < n; j += 8) {
+                    double t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) t[u] = H0[i + (size_t)n * (j + u)];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) W[i + (size_t)n * (j + u)] = t[u];
+                }
+            }
             if (on) W[i + (size_t)n * i] = (H0[i + (size_t)n * i] + aeU_set) - (LF1 * (LF1 * DF1) + LF2 * (LF2 * DF2));
             tcd_ldl(W, n, S, flops);
             const double yF1 = l1 * F1 - mu, yF2 = l2 * F2 - mu;
             const double bU = -Lfu - (LF1 * yF1 + LF2 * yF2);
-            dU = tcd_ldl_solve(W, n, bU, S);
+            dU = tcd_ldl_solve(W, n, on ? bU : 0.0, S);
             d1 = yF1 / DF1 - LF1 * dU;
             d2 = yF2 / DF2 - LF2 * dU;
             hdu = tcd_matvec(H0, n, dU, S);
@@ -545,7 +647,7 @@ template <typename T> static int tcd_alloc(tc_dense *s, T **p, size_t count) {
 }
 
 template <int NT> static int tcd_launch_gram(tc_dense *s) {
-    const size_t smem = (size_t)(NT * 8 + 8) * TCD_LDS * sizeof(double);
+    const size_t smem = 2 * (size_t)(NT * 8 + 8) * TCD_GLDS * sizeof(double);
     TCD_CUDA(cudaFuncSetAttribute(tcd_gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)s->batch, (unsigned)((NT + 7) / 8));
     tcd_gram_kernel<NT><<<grid, TCD_THREADS, smem, s->stream>>>(s->A, s->b, s->N, s->H0, s->g0, s->c0);
@@ -570,7 +672,7 @@ int tc_dense_create(tc_dense **out, int64_t N, int64_t n, int64_t batch, double 
     TCD_TRY((int)cudaEventCreate(&s->ev0));
     TCD_TRY((int)cudaEventCreate(&s->ev1));
     TCD_TRY((int)cudaEventCreate(&s->ev2));
-    s->grid = (int)(batch < s->sms ? batch : s->sms);                    // one CTA per SM (shared memory bound)
+    s->grid = (int)(batch < TCD_CTAS * s->sms ? batch : TCD_CTAS * s->sms);   // several CTAs per SM: one's serial sections overlap the others'
     TCD_TRY(tcd_alloc(s, &s->H0, (size_t)batch * n * n));
     TCD_TRY(tcd_alloc(s, &s->g0, (size_t)batch * n));
     TCD_TRY(tcd_alloc(s, &s->c0, (size_t)batch));

@@ -25,6 +25,9 @@
 #define TC_addEye2HessianMIN 1e-20
 #define TC_maxDirectionError 1e-6
 #define TC_stepback .99
+// equilibrium driver, D.driver == 1: lib/ipmPDeq_CSsolver.c:313-316
+#define TCEQ_addEye2Hessian2MAX 1e-2
+#define TCEQ_maxDirectionError 1e-9
 
 #define TC_MIN(A, B) (((A) < (B)) ? (A) : (B))
 #define TC_MAX(A, B) (((A) > (B)) ? (A) : (B))
@@ -67,6 +70,12 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     const tc_defines &D = P.def;
     const bool hasF = D.nF > 0, hasG = D.nG > 0;
     const bool adjust = D.setAddEye2Hessian && D.adjustAddEye2Hessian;
+    // D.driver == 1: ipmPDeq_CSsolver (lib/ipmPDeq_CSsolver.c:122-802, Nash equilibria with latent variables).  Same loop
+    // skeleton; what differs is marked `eq` below: only the second regulariser is adapted, from the direction error
+    // alone and with up to 20 immediate retries (:333-374); thresholds of the barrier update (:622-651); alphaDualEq
+    // without coupled step sizes (:611); no 2048 status bit.  FN_setAddEye2HessianU/Eq are setAddEye2Hessian1__/2__ and
+    // FN_initDualEqX is initDualEq__ there (tape.py).
+    const bool eq = D.driver == 1;
 
     tc_bT run, updU, updEq, pr, pr2;
     tc_iT status, iter, ls;
@@ -152,7 +161,42 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         }
 
         // ---- regularisation control (:393-548) ----
-        if (adjust) {
+        if (adjust && eq) {                                                 // ipmPDeq_CSsolver.c:318-374
+            TC_FORT { pr[t] = run[t] && updU[t]; pr2[t] = run[t] && updEq[t]; }
+            tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);
+            tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr2);
+            TC_FORT if (run[t]) updU[t] = updEq[t] = false;
+            tc_get(c, P, FN_getDirectionError, run);
+            tc_value(c, P, FN_getDirectionError, 0, run, v1);
+            tc_bT retry;
+            TC_FORT {
+                retry[t] = false;
+                if (run[t]) {
+                    if (v1[t] < TCEQ_maxDirectionError) {
+                        if (aeEq[t] > TC_addEye2HessianMIN) {
+                            aeEq[t] = TC_MAX(.75 * aeEq[t], TC_addEye2HessianMIN);
+                            updEq[t] = true;                                // stored at the next iteration
+                        }
+                    } else retry[t] = true;
+                }
+            }
+            for (int ii = 0; ii < 20; ii++) {                               // :343-372, per instance
+                TC_FORT {
+                    pr[t] = false;
+                    if (retry[t]) {
+                        if (v1[t] >= TCEQ_maxDirectionError && aeEq[t] < TCEQ_addEye2Hessian2MAX) {
+                            aeEq[t] = TC_MIN(2 * TC_MAX(aeEq[t], TC_addEye2HessianMIN), TCEQ_addEye2Hessian2MAX);
+                            pr[t] = true;
+                        } else retry[t] = false;
+                    }
+                }
+                if (!tc_any_tile(pr)) break;
+                tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr);     // immediate
+                tc_get(c, P, FN_getDirectionError, pr);
+                tc_value(c, P, FN_getDirectionError, 0, pr, v2);
+                TC_FORT if (pr[t]) v1[t] = v2[t];
+            }
+        } else if (adjust) {
             TC_FORT { pr[t] = run[t] && updU[t]; pr2[t] = run[t] && updEq[t]; }
             tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);            // delayed from last iteration
             tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr2);
@@ -273,7 +317,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             tc_set_scalar(c, P, FN_setAlphaDualIneq, alphaPrimal, run);
             // mu from the predicted complementarity (sigma = rho^delta), only after a long affine step (:627-660)
             TC_FORT pr[t] = run[t] && alphaPrimal[t] > D.alphaMax / 2 &&
-                            (!hasG || norminf_eq[t] < 100 * D.equalTolerance || norminf_eq[t] < 1e-3);
+                            (!hasG || norminf_eq[t] < 100 * D.equalTolerance || (!eq && norminf_eq[t] < 1e-3));   // eq :377
             tc_get(c, P, FN_getRho, pr);
             tc_value(c, P, FN_getRho, 0, pr, v0);
             TC_FORT if (pr[t]) {
@@ -369,7 +413,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             } else {
                 alphaDualIneq[t] *= TC_stepback;
                 if (alphaDualIneq[t] > alphaMax_[t]) alphaDualIneq[t] = alphaMax_[t];
-                alphaDualEq[t] = alphaDualIneq[t];
+                alphaDualEq[t] = eq ? D.alphaMax : alphaDualIneq[t];         // eq :611
             }
         }
         if (hasG) tc_set_scalar(c, P, FN_setAlphaDualEq, alphaDualEq, run);
@@ -379,7 +423,25 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         // ---- barrier parameter update, skipAffine!=0 (:782-859) ----
         TC_FORT {
             bool set_mu = false, reinit_dual = false;
-            if (run[t] && D.skipAffine) {
+            if (run[t] && D.skipAffine && eq) {                             // ipmPDeq_CSsolver.c:620-660
+                const bool th_grad = norminf_grad[t] < TC_MAX(1e-3, 1e0 * D.gradTolerance);
+                const bool th_eq = !hasG || norminf_eq[t] < TC_MAX(1e-5, 1e0 * D.equalTolerance);
+                if (alphaPrimal[t] > D.alphaMax / 2 && th_grad && th_eq) {
+                    const double r = sqrt(mu[t]);
+                    mu[t] *= TC_MIN(D.muFactorAggressive, r);
+                    if (mu[t] < muMin[t]) mu[t] = muMin[t];
+                    set_mu = true;
+                } else if (alphaPrimal[t] < .02) {
+                    mu[t] *= 1.1;
+                    if (mu[t] > 100 * mu0) mu[t] = 100 * mu0;
+                    set_mu = true;
+                    reinit_dual = true;
+                } else {
+                    mu[t] *= D.muFactorConservative;
+                    if (mu[t] < muMin[t]) mu[t] = muMin[t];
+                    set_mu = true;
+                }
+            } else if (run[t] && D.skipAffine) {
                 const bool th_grad = norminf_grad[t] < TC_MAX(1e-6, 1e0 * D.gradTolerance);
                 const bool th_eq = !hasG || norminf_eq[t] < TC_MAX(1e-5, 1e0 * D.equalTolerance);
                 if (alphaPrimal[t] > alphaMax_[t] / 2 && th_grad && th_eq) {
@@ -440,7 +502,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
                     status[t] |= 1024;
             }
         }
-        TC_FORT if (adjust && diag[t] && aeU[t] > D.addEye2HessianUtolerance) status[t] |= 2048;
+        TC_FORT if (adjust && !eq && diag[t] && aeU[t] > D.addEye2HessianUtolerance) status[t] |= 2048;
     }
     TC_FORT {
         status_out[t] = status[t];

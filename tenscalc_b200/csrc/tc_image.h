@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include <vector_types.h>
 
-#define TC_MAGIC 0x3030324243540004LL
+#define TC_MAGIC 0x3030324243540005LL
 #define TC_CONST_BIT 0x40000000u   // io[] words (get/copy sources): constant-pool index
 #define TC_SLOT_MASK 0x3FFFFFFFu
 #define TC_NO_SLOT 0xFFFFFFFFu
@@ -69,6 +69,7 @@ struct tc_defines {         // the #define table of lib/cmex2optimizeCS.m:303-33
     int32_t nU, nG, nF;
     int32_t scaleCost, scaleInequalities, coupledAlphas, setAddEye2Hessian, adjustAddEye2Hessian,
         useInertia, skipAffine, delta;
+    int32_t driver;         // 0: ipmPD_CSsolver (lib/ipmPD_CSsolver.c), 1: ipmPDeq_CSsolver (lib/ipmPDeq_CSsolver.c)
     double gradTolerance, addEye2HessianUtolerance, equalTolerance, desiredDualityGap, alphaMin,
         alphaMax, muFactorAggressive, muFactorConservative;
 };

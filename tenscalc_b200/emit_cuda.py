@@ -283,7 +283,10 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         for k in total:
             total[k] += st[k]
     copy_calls: Dict[int, List[str]] = {}
-    for name, fid in FN.items():
+    from .tape import driver_of, fn_items
+    if driver_of(pr) != "ipmPD_CSsolver" and driver != "warp":
+        raise ValueError("the lane-decoupled and work-queue drivers implement ipmPD_CSsolver only")
+    for name, fid in fn_items(pr):
         if name in pr.copies:
             fs = emit_copy(pr, fid, name)
             funcs += fs

@@ -188,3 +188,117 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
                     n_groups=len(problem.groups), n_slots=problem.n_slots,
                     dense_block=ldl_dense_block(fac))
     return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)
+
+
+# ------------------------------------------------------------------------------------------------
+# Nash equilibria with latent variables: cmex2equilibriumLatentCS -> ipmPDeq_CSsolver
+# ------------------------------------------------------------------------------------------------
+def equilibrium_defines(nU: int, nD: int, nX: int, nG: int, nF: int, nNu: int, *, gradTolerance: float = 1e-4,
+                        equalTolerance: float = 1e-4, desiredDualityGap: float = 1e-5, alphaMin: float = 1e-7,
+                        alphaMax: float = 1.0, coupledAlphas: bool = True, muFactorAggressive: float = .2,
+                        muFactorConservative: float = .95, skipAffine: bool = True, delta: int = 3,
+                        scaleInequalities: bool = True, scaleCost: float = 0.0, scaleEqualities: bool = False,
+                        addEye2Hessian: bool = False, adjustAddEye2Hessian: bool = False,
+                        addEye2Hessian1tolerance: float = 1e-6, useLDL: bool = False, smallerNewtonMatrix: bool = False,
+                        solverVerboseLevel: int = 1, **ignored) -> Dict[str, object]:
+    """the #define table cmex2equilibriumLatentCS hands to ipmPDeq_CSsolver.c (lib/cmex2equilibriumLatentCS.m:417-448;
+    defaults lib/private/parameters4equilibrium.m, parameters4all.m).  ``driver`` (not a reference define) tells the
+    device image which solver loop to run; nU/nG/nF/addEye2HessianUtolerance are the names the device driver reads."""
+    return dict(
+        nZ=int(nU + nD + nX), nU=int(nU), nD=int(nD), nX=int(nX), nG=int(nG), nF=int(nF), nNu=int(nNu),
+        gradTolerance=float(gradTolerance), addEye2Hessian1tolerance=float(addEye2Hessian1tolerance),
+        addEye2HessianUtolerance=float(addEye2Hessian1tolerance),
+        equalTolerance=float(equalTolerance), desiredDualityGap=float(desiredDualityGap),
+        scaleCost=int(scaleCost != 0), scaleInequalities=int(bool(scaleInequalities)),
+        scaleEqualities=int(bool(scaleEqualities)),
+        alphaMin=float(alphaMin), alphaMax=float(alphaMax), coupledAlphas=int(bool(coupledAlphas)),
+        setAddEye2Hessian=int(bool(addEye2Hessian)), adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)),
+        useInertia=0, muFactorAggressive=float(muFactorAggressive),
+        muFactorConservative=float(muFactorConservative), delta=int(delta), skipAffine=int(bool(skipAffine)),
+        smallerNewtonMatrix=int(bool(smallerNewtonMatrix)), useLDL=int(bool(useLDL)), useUmfpack=0, allowSave=0,
+        debugConvergence=0, profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)), driver="ipmPDeq_CSsolver")
+
+
+def cmex2equilibriumLatentCS(*, classname: str, P1objective: Tcalculus, P2objective: Tcalculus,
+                             P1optimizationVariables: Sequence[Tcalculus], P2optimizationVariables: Sequence[Tcalculus],
+                             latentVariables: Sequence[Tcalculus] = (), P1constraints: Sequence[Constraint] = (),
+                             P2constraints: Sequence[Constraint] = (), latentConstraints: Sequence[Constraint] = (),
+                             outputExpressions: Union[Sequence[Tcalculus], Dict[str, Tcalculus]] = (),
+                             parameters: Sequence[Tcalculus] = (), ordering=None, **options) -> GeneratedSolver:
+    """``cmex2equilibriumLatentCS`` (lib/cmex2equilibriumLatentCS.m:1-596): generates the solver of the two-player
+    Nash equilibrium with latent variables described in ``ipm_builder_eq``; the generated class has the usual
+    ``setP_*/setV_*/solve/getOutputs`` surface and its ``solve`` runs ``ipmPDeq_CSsolver`` (lib/ipmPDeq_CSsolver.c).
+    Options as in the reference (``addEye2Hessian``, ``adjustAddEye2Hessian`` and ``useLDL`` default to false)."""
+    from .ipm_builder_eq import build_ipm_eqlat
+    if options.get("adjustAddEye2Hessian") and not options.get("addEye2Hessian"):
+        raise ValueError("adjustAddEye2Hessian needs addEye2Hessian")
+    if options.get("useUmfpack"):
+        raise NotImplementedError("useUmfpack=true (atomic factorisation) is not built")
+    tab = T.table()
+    code = CSparse(tab)
+    if P1objective.numel() != 1 or P2objective.numel() != 1:
+        raise ValueError("objectives must be scalars")
+    par_info = []
+    for p in parameters:
+        nm = _name_of(p)
+        code.declare_set(f"setP_{nm}", p.flat(), p.shape, kind="parameter")
+        par_info.append((nm, p.shape))
+    var_info = []
+
+    def pack(vars_: Sequence[Tcalculus]):
+        ids, store = [], []
+        for v in vars_:
+            nm = _name_of(v)
+            e = v.flat()
+            st = [tab.new_set(f"{nm}_init[{k}]") for k in range(len(e))]
+            code.declare_set(f"setV_{nm}", st, v.shape, kind="variable")
+            ids += e
+            store += st
+            var_info.append((nm, v.shape))
+        return ids, store
+
+    u, u0 = pack(P1optimizationVariables)                     # :230-246 / packVariables.m
+    d, d0 = pack(P2optimizationVariables)
+    x, x0 = pack(latentVariables)
+    if len(set(u + d + x)) != len(u + d + x):
+        raise ValueError("optimisation and latent variables must be distinct")
+    code.declare_copy("initPrimal__", u + d + x, u0 + d0 + x0)   # :303
+
+    def parse(cons, what):
+        Gs: List[Optional[int]] = []
+        Fs: List[Optional[int]] = []
+        for c in cons:
+            if not isinstance(c, Constraint):
+                raise ValueError(f"{what} constraint is not a Tcalculus comparison")
+            (Gs if c.kind == "iszero" else Fs).extend(c.expr.flat())
+        return Gs, Fs
+
+    Gu, Fu = parse(P1constraints, "P1")                       # :252-262
+    Gd, Fd = parse(P2constraints, "P2")
+    H, Herr = parse(latentConstraints, "latent")
+    if Herr:
+        raise ValueError("latent constraints cannot be inequalities (cmex2equilibriumLatentCS.m:273-276)")
+    mk = lambda nm, n: [tab.new_set(f"{nm}[{k}]") for k in range(n)]     # noqa: E731
+    P1nu, P1lam = mk("P1nu_", len(Gu)), mk("P1lambda_", len(Fu))
+    P2nu, P2lam = mk("P2nu_", len(Gd)), mk("P2lambda_", len(Fd))
+    P1xnu, P2xnu = mk("P1xnu_", len(H)), mk("P2xnu_", len(H))
+    keys = ("scaleInequalities", "scaleCost", "addEye2Hessian", "skipAffine", "useLDL", "smallerNewtonMatrix")
+    info = build_ipm_eqlat(code, u, d, x, P1objective.e[()], P2objective.e[()], Fu, Fd, Gu, Gd, H, P1lam, P2lam, P1nu,
+                           P2nu, P1xnu, P2xnu, ordering=ordering, **{k: options[k] for k in keys if k in options})
+    is_struct = isinstance(outputExpressions, dict)
+    items = list(outputExpressions.items()) if is_struct else [(f"y{k + 1}", e) for k, e in enumerate(outputExpressions)]
+    out_info, srcs, shapes, names = [], [], [], []
+    for nm, e in items:
+        e = Tcalculus._lift(e)
+        srcs.append(e.flat())
+        shapes.append(e.shape)
+        names.append(nm)
+        out_info.append((nm, e.shape))
+    code.declare_get("getOutputs", srcs, shapes, names)
+    defines = equilibrium_defines(len(u), len(d), len(x), info["nG"], info["nF"], info["nNu"], **options)
+    problem = code.compile(defines)
+    fac = info["factor"]
+    gen_info = dict(ordering="lu threshold pivoting" if not options.get("useLDL") else "symamd (normal equations)",
+                    nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
+                    n_groups=len(problem.groups), n_slots=problem.n_slots, driver="ipmPDeq_CSsolver")
+    return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)

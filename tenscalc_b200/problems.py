@@ -195,7 +195,56 @@ def isa_probe(N: int = 60, **opts) -> Tuple[GeneratedSolver, dict]:
     return gen, dict(mu0=1.0, maxIter=60)
 
 
-BUILDERS = dict(sls=sls, l1l2=l1l2, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter, isa_probe=isa_probe)
+# ------------------------------------------------------------------------------------------------
+# zero-sum games of examples/TCgames.m, generated with cmex2equilibriumLatentCS -> ipmPDeq_CSsolver
+# ------------------------------------------------------------------------------------------------
+def matrix_game(N1: int = 10, N2: int = 6, **opts) -> Tuple[GeneratedSolver, dict]:
+    """mixed saddle point of a matrix game, examples/TCgames.m:29-98 (N1=50, N2=20 there)"""
+    from .optimize import cmex2equilibriumLatentCS
+    T.clear()
+    A1 = Tvariable("A1", [N1, N2])
+    u = Tvariable("u", N1)
+    d = Tvariable("d", N2)
+    J1 = (u @ A1) @ d
+    gen = cmex2equilibriumLatentCS(classname="tmp_matrixsaddle", P1objective=J1, P2objective=-J1,
+                                   P1optimizationVariables=[u], P2optimizationVariables=[d],
+                                   P1constraints=[tsum(u, 0) == 1, u >= 0], P2constraints=[tsum(d, 0) == 1, d >= 0],
+                                   outputExpressions=[u, d, J1], parameters=[A1], **opts)
+    return gen, dict(mu0=1.0, maxIter=30)
+
+
+def qsaddle(N: int = 20, latent: bool = False, **opts) -> Tuple[GeneratedSolver, dict]:
+    """saddle point of a quadratic zero-sum cost with bounded policies, examples/TCgames.m:104-147, and the same
+    problem written with a latent (state) variable x = u + d, :155-214.  The constant 2 of the script is the
+    parameter ``target`` here, so that a batch holds different instances."""
+    from .optimize import cmex2equilibriumLatentCS
+    T.clear()
+    u = Tvariable("u", N)
+    d = Tvariable("d", N)
+    target = Tvariable("target", N)
+    if latent:
+        x = Tvariable("x", N)
+        Ju = norm2(x - target) - 10 * norm2(d)
+        gen = cmex2equilibriumLatentCS(classname="tmp_qsaddlestate", P1objective=Ju, P2objective=-Ju,
+                                       P1optimizationVariables=[u], P2optimizationVariables=[d], latentVariables=[x],
+                                       P1constraints=[u >= -1, u <= 1], P2constraints=[d >= -1, d <= 1],
+                                       latentConstraints=[x == u + d], outputExpressions=[u, d, x, Ju],
+                                       parameters=[target], **opts)
+    else:
+        Ju = norm2(u + d - target) - 10 * norm2(d)
+        gen = cmex2equilibriumLatentCS(classname="tmp_qsaddle", P1objective=Ju, P2objective=-Ju,
+                                       P1optimizationVariables=[u], P2optimizationVariables=[d],
+                                       P1constraints=[u >= -1, u <= 1], P2constraints=[d >= -1, d <= 1],
+                                       outputExpressions=[u, d, Ju], parameters=[target], **opts)
+    return gen, dict(mu0=1.0, maxIter=30)
+
+
+def qsaddle_latent(N: int = 20, **opts) -> Tuple[GeneratedSolver, dict]:
+    return qsaddle(N, latent=True, **opts)
+
+
+BUILDERS = dict(sls=sls, l1l2=l1l2, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter, isa_probe=isa_probe,
+                matrix_game=matrix_game, qsaddle=qsaddle, qsaddle_latent=qsaddle_latent)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -265,6 +314,18 @@ def synthetic_inputs(name: str, gen: GeneratedSolver, batch: int, seed: int = 0)
         a[:, -1] = a[:, -2]
         u = a + b_drag * v - np.array([0, 0, 9.8])[:, None, None]
         V = dict(p=p, u=u, positive2=np.ones((T_, B)))
+    elif name == "matrix_game":
+        N1, N2 = dict(gen.parameters)["A1"]
+        P = dict(A1=rng.random((N1, N2, B)))
+        V = dict(u=np.full((N1, B), 1. / N1), d=np.full((N2, B), 1. / N2))
+    elif name in ("qsaddle", "qsaddle_latent"):
+        N = dict(gen.parameters)["target"][0]
+        P = dict(target=rng.uniform(0, 3, (N, B)))
+        u0 = rng.uniform(-.5, .5, (N, B))
+        d0 = rng.uniform(-.5, .5, (N, B))
+        V = dict(u=u0, d=d0)
+        if name == "qsaddle_latent":
+            V["x"] = u0 + d0
     elif name == "isa_probe":
         N, n = dict(gen.parameters)["A"]
         P = dict(c=rng.uniform(.5, 1.5, (n, B)), A=rng.random((N, n, B)), b=rng.random((N, B)))

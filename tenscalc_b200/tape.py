@@ -48,7 +48,7 @@ from . import itable as it
 from .csparse import CompiledProblem
 from .optimize import GeneratedSolver
 
-MAGIC = 0x3030324243540004  # "\x03\0TCB200" little-endian tag + format version
+MAGIC = 0x3030324243540005  # "\x03\0TCB200" little-endian tag + format version
 CONST_BIT = 1 << 30         # io[] words only (get/copy sources): constant-pool index
 NO_SLOT = 0xFFFFFFFF
 
@@ -85,6 +85,20 @@ FN = {name: k for k, name in enumerate([
     "setAlphaDualIneq__", "updatePrimalDual__", "getJ__", "getOutputs",
     "getMaxAlphas_a__", "getMinF_a__", "getRho__"])}
 FN_USER0 = len(FN)
+# the equilibrium driver (lib/ipmPDeq_CSsolver.c:28-52) calls three of the slots by other names
+EQ_NAMES = {"setAddEye2HessianU__": "setAddEye2Hessian1__", "setAddEye2HessianEq__": "setAddEye2Hessian2__",
+            "initDualEqX__": "initDualEq__"}
+DRIVERS = {"ipmPD_CSsolver": 0, "ipmPDeq_CSsolver": 1}
+
+
+def driver_of(pr: CompiledProblem) -> str:
+    return str((pr.defines or {}).get("driver", "ipmPD_CSsolver"))
+
+
+def fn_items(pr: CompiledProblem):
+    """(name of the function in THIS problem, driver function id) for every slot of the FN table"""
+    eq = driver_of(pr) == "ipmPDeq_CSsolver"
+    return [((EQ_NAMES.get(name, name) if eq else name), fid) for name, fid in FN.items()]
 KIND_NONE, KIND_SET, KIND_GET, KIND_COPY = 0, 1, 2, 3
 
 
@@ -352,7 +366,7 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
     def src_word(x) -> int:
         return NO_SLOT if x is None else io_word(x)
 
-    for name, fid in FN.items():
+    for name, fid in fn_items(pr):
         if name in pr.sets:
             s = pr.sets[name]
             put(fid, KIND_SET, [], s.children, [int(slot[d]) for d in s.dest])
@@ -398,6 +412,9 @@ def serialize(gen: GeneratedSolver) -> bytes:
     ih[16:19] = (d["nU"], d["nG"], d["nF"])
     ih[19:27] = (d["scaleCost"], d["scaleInequalities"], d["coupledAlphas"], d["setAddEye2Hessian"],
                  d["adjustAddEye2Hessian"], d["useInertia"], d["skipAffine"], d["delta"])
+    ih[27] = DRIVERS[str(d.get("driver", "ipmPD_CSsolver"))]
+    if ih[27] == 1:
+        ih[16] = d["nZ"]          # the device driver only tests nG > 0 / nF > 0 and divides by nF
     dh = np.zeros(16, dtype=np.float64)
     dh[0:8] = (d["gradTolerance"], d["addEye2HessianUtolerance"], d["equalTolerance"], d["desiredDualityGap"],
                d["alphaMin"], d["alphaMax"], d["muFactorAggressive"], d["muFactorConservative"])

@@ -17,7 +17,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-CASES = dict(sls=24, mpc_dcmotor=24, l1l2=6, mpc_quadcopter=6, isa_probe=24)
+CASES = dict(sls=24, mpc_dcmotor=24, l1l2=6, mpc_quadcopter=6, isa_probe=24,
+             matrix_game=24, qsaddle=24, qsaddle_latent=24)     # ipmPDeq_CSsolver (examples/TCgames.m)
 SEED = 2024
 
 

@@ -365,7 +365,7 @@ def _emulate_cells(L, g, m, consts, ring_size):
                         m[wr // tp.TILE_BYTES] = acc
 
 
-@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor", "mpc_quadcopter", "isa_probe"])
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor", "mpc_quadcopter", "isa_probe", "qsaddle_latent"])
 def test_cell_tape_equals_instruction_semantics(name):
     """every group: numpy model of the kernel's cell machine (with its look-ahead operand fetch)
     vs direct evaluation of the reference instruction forms (oracle/pyeval.py), bit for bit"""

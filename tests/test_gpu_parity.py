@@ -22,7 +22,13 @@ CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_qu
          ("sls", 512, AFFINE), ("mpc_dcmotor", 512, AFFINE), ("mpc_dcmotor", 512, {**AFFINE, "smallerNewtonMatrix": True}),
          ("mpc_quadcopter", 256, {"T_": 20, **AFFINE}),
          # every unary opcode of the ISA (instructionsTableUTHash.c:1347-1539) and multi-line sums of products
-         ("isa_probe", 512, {})]
+         ("isa_probe", 512, {}),
+         # Nash equilibria: cmex2equilibriumLatentCS -> ipmPDeq_CSsolver (lib/ipmPDeq_CSsolver.c, examples/TCgames.m),
+         # non-symmetric Newton matrix factored by the fixed-pattern LU; oracle = the reference's unmodified driver
+         ("matrix_game", 512, {}), ("qsaddle", 512, {}), ("qsaddle_latent", 512, {}),
+         ("qsaddle", 256, {"useLDL": True}),                                  # normal equations + LDL' (ipmPDeqlat_CS.m:645-651)
+         ("matrix_game", 256, {"skipAffine": False}),
+         ("qsaddle", 256, {"addEye2Hessian": True, "adjustAddEye2Hessian": True})]     # regulariser retries (:318-374)                         # affine-scaling step of the eq driver (:326-398)
 
 
 def _oracle(gen, name):

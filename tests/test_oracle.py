@@ -55,7 +55,12 @@ def test_port_reproduces_reference_golden(name):
         assert np.array_equal(v, g["out_" + k]), f"{name}.{k} not bit-identical to the reference"
 
 
-@pytest.mark.parametrize("name", NAMES)
+# equilibrium problems (cmex2equilibriumLatentCS -> the reference's unmodified lib/ipmPDeq_CSsolver.c); that driver
+# is not restated as a port: the compiled reference library is the only oracle
+EQ_NAMES = ["matrix_game", "qsaddle", "qsaddle_latent"]
+
+
+@pytest.mark.parametrize("name", NAMES + EQ_NAMES)
 def test_compiled_reference_reproduces_golden(name):
     from oracle.oracle import Oracle
     gen, _ = generated(name)
@@ -67,6 +72,31 @@ def test_compiled_reference_reproduces_golden(name):
     assert np.array_equal(st, g["status"]) and np.array_equal(it, g["iter"])
     for k, v in out.items():
         assert np.array_equal(v, g["out_" + k])
+
+
+def test_equilibrium_solutions_are_saddle_points():
+    """closed-form checks of the golden equilibrium fixtures: the quadratic game min_u max_d |u+d-t|^2-10|d|^2 on the
+    box [-1,1]^N has u=min(t,1)-d... per coordinate: d=(u-t)/9 and u=clip(t-d) -- and the mixed policies of the
+    matrix game are probability vectors whose value no pure strategy improves (examples/TCgames.m:29-147)"""
+    g = _load("qsaddle")
+    n = g["out_y1"].shape[0]
+    t = g["P"].T
+    u, d = g["out_y1"], g["out_y2"]
+    assert (g["status"] == 0).all()
+    assert np.abs(d - (u - t) / 9).max() < 1e-4
+    assert np.abs(u - np.clip(t - d, -1, 1)).max() < 2e-3        # interior-point accuracy at the kink
+    gl = _load("qsaddle_latent")
+    assert (gl["status"] == 0).all() and np.abs(gl["out_y3"] - (gl["out_y1"] + gl["out_y2"])).max() < 1e-4
+    assert np.abs(gl["out_y1"] - u).max() < 1e-3 and np.abs(gl["out_y2"] - d).max() < 1e-3   # same game, latent form
+    m = _load("matrix_game")
+    u, d, v = m["out_y1"], m["out_y2"], m["out_y3"]
+    N1, N2 = u.shape[0], d.shape[0]
+    A = m["P"].reshape(-1, N2, N1).transpose(2, 1, 0)            # [N1, N2, B] (column-major per instance)
+    assert (m["status"] == 0).all()
+    assert np.abs(u.sum(0) - 1).max() < 1e-4 and np.abs(d.sum(0) - 1).max() < 1e-4 and u.min() > 0 and d.min() > 0
+    Ad = np.einsum("ijb,jb->ib", A, d)                           # P1 minimises: no row does better than the value
+    uA = np.einsum("ib,ijb->jb", u, A)                           # P2 maximises: no column does better
+    assert (Ad.min(0) > v - 1e-3).all() and (uA.max(0) < v + 1e-3).all()
 
 
 def test_golden_status_zero_on_examples():
