@@ -217,15 +217,22 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             src.append("TC_TILE_LOOP {")
             src.append("double *__restrict__ mt = TC_MT;")
             src += [f"const double v{q}=mt[{int(slot[q]) * TILE}];" for q in loads]
-            if prefetch and k + 1 < len(bodies):
-                # while this chunk's operands are in flight, pull the NEXT chunk's operands into L2: its
-                # load phase then costs an L2 hit instead of an HBM round trip (no registers involved)
-                mine = {int(slot[q]) for q in loads} | stores
-                nxt = [int(slot[q]) for q in bodies[k + 1][1] if int(slot[q]) not in mine]
-                if nxt:            # the clobber keeps this chunk's own loads ahead of the prefetches
-                    src.append('asm volatile("" ::: "memory");')
-                src += [f"TC_PREFETCH(mt+{sl * TILE});" for sl in nxt]
-                stats["prefetches"] += len(nxt)
+            # while this chunk's operands are in flight, pull the operands of the chunk `prefetch` positions ahead
+            # into L2: its load phase then costs an L2 hit instead of an HBM round trip (no registers involved);
+            # with a distance above 1 the first chunks of the group also cover the chunks in between
+            targets = [k + prefetch] if prefetch else []
+            if prefetch > 1 and k == 0:
+                targets = list(range(1, prefetch + 1))
+            nxt: List[int] = []
+            mine = {int(slot[q]) for q in loads} | stores
+            for kt in targets:
+                if kt < len(bodies):
+                    between = set().union(*[bodies[j][2] for j in range(k + 1, kt)]) if kt > k + 1 else set()
+                    nxt += [int(slot[q]) for q in bodies[kt][1] if int(slot[q]) not in mine and int(slot[q]) not in between]
+            if nxt:                # the clobber keeps this chunk's own loads ahead of the prefetches
+                src.append('asm volatile("" ::: "memory");')
+                src += [f"TC_PREFETCH(mt+{sl * TILE});" for sl in dict.fromkeys(nxt)]
+                stats["prefetches"] += len(set(nxt))
             src += lines
             src.append("}")
         src.append("}")
