@@ -609,6 +609,10 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION, the default of some
+    # images) out of it; an explicit INFO/TRACE setting of the caller is respected
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

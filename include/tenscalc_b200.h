@@ -69,7 +69,10 @@ int64_t tc_scratch_bytes(const tc_solver *s);
 int tc_set(tc_solver *s, int set_index, const double *values, int64_t batch_stride);
 int tc_set_device(tc_solver *s, int set_index, const double *d_values, int64_t batch_stride);
 
-/* ipmPD_CSsolver for every instance.  Inputs by pointer as in the reference; `status` and
+/* ipmPD_CSsolver -- or ipmPDeq_CSsolver / ipmPDminmax_CSsolver, whichever driver the class was generated for
+ * (lib/ipmPDeq_CSsolver.c:122-131, lib/ipmPDminmax_CSsolver.m:1) -- for every instance.  `addEye2Hessian` is
+ * double[2] = {U, Eq} ({1, 2} for equilibrium classes) and double[3] = {U, D, Eq} for min-max classes.
+ * Inputs by pointer as in the reference; `status` and
  * `iter` are int32[batch]; `time` receives the device time of the whole batch in seconds.
  * tc_solve copies status/iter to host memory; tc_solve_device leaves them on the device and
  * does not synchronise the host (`time` may be NULL). */

@@ -22,6 +22,10 @@ EQ_CONFIGS = [("matrix_game", {}), ("qsaddle", {}), ("qsaddle_latent", {}), ("qs
 EXTRA = [("mpc_quadcopter", {}, "-O0", ""), ("mpc_quadcopter", {}, "-O2", ""), ("mpc_quadcopter", {}, "-O1", "crpow")]
 
 
+# ipmPDminmax_CSsolver (min-max): PARITY UNPINNED port of the MATLAB solver, both kinds include it
+MM_CONFIGS = [("minmax_box", {}), ("minmax_box_latent", {}), ("minmax_box", {"N": 16})]
+
+
 def _one(args):
     name, kw, kind, opt, variant = args
     from tenscalc_b200 import problems
@@ -43,7 +47,7 @@ def build_all(kinds=("ref", "port"), configs=CONFIGS, workers=4, extra=True):
             print("oracle dense_ls", N, n, k, DenseOracle(N, n, lo, hi, k).build())
     jobs = [(n, kw, k, "-O1", "") for n, kw in configs for k in kinds]
     if "ref" in kinds:
-        jobs += [(n, kw, "ref", "-O1", "") for n, kw in EQ_CONFIGS]
+        jobs += [(n, kw, "ref", "-O1", "") for n, kw in EQ_CONFIGS + MM_CONFIGS]
     if extra:
         jobs += [(n, kw, kinds[0], opt, var) for n, kw, opt, var in EXTRA]
     with ProcessPoolExecutor(workers) as ex:

@@ -37,7 +37,8 @@ def _run_slice(args):
     status = np.zeros(B, dtype=np.int32)
     it = np.zeros(B, dtype=np.int32)
     sec = np.zeros(B)
-    ae = np.asarray(addEye, dtype=np.float64)
+    ae = list(addEye)
+    ae = np.asarray(ae + [ae[-1]] * (3 - len(ae)), dtype=np.float64)     # the generated runners read three entries
     Pp = np.ascontiguousarray(Pp)
     Vp = np.ascontiguousarray(Vp)
     t0 = time.perf_counter()

@@ -41,7 +41,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 MAX_PER_FUNCTION = 200
 
-_DOUBLE_DEFINES = ("gradTolerance", "addEye2HessianUtolerance", "addEye2Hessian1tolerance", "equalTolerance", "desiredDualityGap",
+_DOUBLE_DEFINES = ("gradTolerance", "addEye2HessianUtolerance", "addEye2Hessian1tolerance", "addEye2HessianDtolerance", "equalTolerance", "desiredDualityGap",
                    "alphaMin", "alphaMax", "muFactorAggressive", "muFactorConservative")
 
 
@@ -231,7 +231,9 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
         if name not in pr.gets:
             w(f"static void {name}({sig}) {{ *mp=0; *mn=0; }}\n")
 
-    if driver == "ref":
+    if solver == "ipmPDminmax_CSsolver":    # PARITY UNPINNED: transcription of the reference's MATLAB solver (see that file)
+        w(f'#include "{os.path.join(HERE, "ipm_driver_minmax_port.c")}"\n')
+    elif driver == "ref":
         w(f'#include "/root/reference/lib/{solver}.c"\n')
     elif solver != "ipmPD_CSsolver":
         raise NotImplementedError(f"{solver}: only the reference's own driver is used as oracle (kind='ref')")
@@ -247,7 +249,7 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
       "    int32_t saveIter,const double *addEye,int32_t *status,int32_t *iter,double *Y,double *seconds) {\n"
       f"  const int64_t nP={sum(n for _, n in npar)},nV={sum(n for _, n in nvar)},nY={sum(nout)};\n"
       "  for (int64_t b=0;b<B;b++) {\n    const double *p=P+b*nP,*v=V+b*nV; double *y=Y+b*nY;\n"
-      "    double mu=mu0,ae[2]={addEye[0],addEye[1]},t; int32_t mi=maxIter,si=saveIter;\n")
+      "    double mu=mu0,ae[3]={addEye[0],addEye[1],addEye[2]},t; int32_t mi=maxIter,si=saveIter;\n")
     off = 0
     for f, n in npar:
         w(f"    {f}(p+{off});\n")

@@ -105,7 +105,8 @@ class Oracle:
         status = np.zeros(B, dtype=np.int32)
         it = np.zeros(B, dtype=np.int32)
         sec = np.zeros(B)
-        ae = np.asarray(addEye2Hessian, dtype=np.float64)
+        ae = list(addEye2Hessian)
+        ae = np.asarray(ae + [ae[-1]] * (3 - len(ae)), dtype=np.float64)      # {U, Eq} or, min-max, {U, D, Eq}
         dp = ctypes.POINTER(ctypes.c_double)
         ip = ctypes.POINTER(ctypes.c_int32)
         lib.oracle_run_batch(B, Pp.ctypes.data_as(dp), Vp.ctypes.data_as(dp), mu0, maxIter, saveIter,

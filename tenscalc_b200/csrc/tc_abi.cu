@@ -395,7 +395,14 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     D.setAddEye2Hessian = (int32_t)ih[22]; D.adjustAddEye2Hessian = (int32_t)ih[23];
     D.useInertia = (int32_t)ih[24]; D.skipAffine = (int32_t)ih[25]; D.delta = (int32_t)ih[26];
     D.driver = (int32_t)ih[27];
-    if (D.driver != 0 && D.driver != 1) { tc_destroy(s); return TC_EFORMAT; }
+    if (D.driver < 0 || D.driver > 2) { tc_destroy(s); return TC_EFORMAT; }
+    D.mpUdesired = (int32_t)ih[28]; D.mnDdesired = (int32_t)ih[29]; D.pad_ = 0;
+    D.addEye2HessianDtolerance = dh[8];
+    if (D.driver == 2 && (n_funcs <= FN_getHessUinertia || (D.setAddEye2Hessian && D.adjustAddEye2Hessian &&
+                                                            !funcs[FN_getHessUinertia].io_cnt))) {
+        tc_destroy(s);
+        return TC_EFORMAT;
+    }
     D.gradTolerance = dh[0]; D.addEye2HessianUtolerance = dh[1]; D.equalTolerance = dh[2];
     D.desiredDualityGap = dh[3]; D.alphaMin = dh[4]; D.alphaMax = dh[5];
     D.muFactorAggressive = dh[6]; D.muFactorConservative = dh[7];
@@ -583,12 +590,17 @@ int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, con
     TC_CUDA(cudaEventRecord(s->ev0, s->stream));
     s->last_iter = d_iter;
     const bool phased = s->phased && (!s->module || s->mod_phased) && !s->img.queue && s->cmp.n_slots > 0;
+    // regularisers: {U, Eq} for ipmPD_CSsolver / {1, 2} for ipmPDeq_CSsolver; the min-max solver takes {U, D, Eq}
+    // (ipmPDminmax_CSsolver.m:46-60)
+    const bool mm = s->img.def.driver == 2;
+    const double aeU = addEye2Hessian[0], aeEq = mm ? addEye2Hessian[2] : addEye2Hessian[1];
+    s->img.aeD0 = mm ? addEye2Hessian[1] : 0.0;
     auto launch = [&](int first, int iters) -> int {
         if (s->module)
-            return s->mod_solve(&s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter,
+            return s->mod_solve(&s->img, *mu0, *maxIter, aeU, aeEq, d_status, d_iter,
                                 (void *)s->stream, first, iters);
         tc_solve_kernel<<<(unsigned)(s->stride / TC_BLOCK), TC_BLOCK, 0, s->stream>>>(
-            s->img, *mu0, *maxIter, addEye2Hessian[0], addEye2Hessian[1], d_status, d_iter, first, iters);
+            s->img, *mu0, *maxIter, aeU, aeEq, d_status, d_iter, first, iters);
         return (int)cudaGetLastError();
     };
     if (!phased) {

@@ -46,9 +46,9 @@ enum { AF_DONE = 0, AF_TRYMAX, AF_TRYMIN, AF_SCAN };
 // one warp.  The per-instance sequence of operations -- hence every rounding -- is unchanged.
 // phase_iters == 0: the whole solve in this launch (tape interpreter, lanes/queue drivers).
 enum { PS_aeU = 0, PS_aeEq, PS_mu, PS_muMin, PS_gapTol, PS_alphaMax, PS_alphaPrimal, PS_alphaDualEq, PS_alphaDualIneq,
-       PS_mp, PS_mn };                                     // TC_PS_ND doubles per column
-enum { PS_iter = 0, PS_flags };                            // TC_PS_NI ints; flags: 1 running, 2 updU, 4 updEq
-static_assert(PS_mn + 1 == TC_PS_ND && PS_flags + 1 == TC_PS_NI, "phase-state layout");
+       PS_mp, PS_mn, PS_aeD };                             // TC_PS_ND doubles per column
+enum { PS_iter = 0, PS_flags };                            // TC_PS_NI ints; flags: 1 running, 2 updU, 4 updEq, 8 updD
+static_assert(PS_aeD + 1 == TC_PS_ND && PS_flags + 1 == TC_PS_NI, "phase-state layout");
 
 typedef double tc_dT[TC_TILES];
 typedef bool tc_bT[TC_TILES];
@@ -77,13 +77,18 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     // FN_initDualEqX is initDualEq__ there (tape.py).
     const bool eq = D.driver == 1;
 
-    tc_bT run, updU, updEq, pr, pr2;
+    // D.driver == 2: ipmPDminmax_CSsolver (lib/ipmPDminmax_CSsolver.m:1-587; its C namesake is stale in the reference,
+    // so the MATLAB solver is the specification and parity with the reference is UNPINNED): a third regulariser for the
+    // maximiser's block, regulariser control from two inertias and the direction error with up to 30 immediate
+    // retries (:238-301), other barrier thresholds (:411-440), 2048 bit from either tolerance (:503-507).
+    const bool mm = D.driver == 2;
+    tc_bT run, updU, updEq, updD, pr, pr2;
     tc_iT status, iter, ls;
-    tc_dT aeU, aeEq, mu, muMin, gapTol, alphaMax_, alphaPrimal, alphaDualEq, alphaDualIneq;
+    tc_dT aeU, aeEq, aeD, mu, muMin, gapTol, alphaMax_, alphaPrimal, alphaDualEq, alphaDualIneq;
     tc_dT norminf_grad, norminf_eq, gap, ineq, ineq1, dual, v0, v1, v2, mp, mn;
     TC_FORT {
-        run[t] = valid[t]; updU[t] = updEq[t] = false; status[t] = 0; iter[t] = 0; ls[t] = LS_DONE;
-        aeU[t] = aeU0; aeEq[t] = aeEq0; mu[t] = mu0; muMin[t] = 0; gapTol[t] = D.desiredDualityGap;
+        run[t] = valid[t]; updU[t] = updEq[t] = updD[t] = false; status[t] = 0; iter[t] = 0; ls[t] = LS_DONE;
+        aeU[t] = aeU0; aeEq[t] = aeEq0; aeD[t] = P.aeD0; mu[t] = mu0; muMin[t] = 0; gapTol[t] = D.desiredDualityGap;
         alphaMax_[t] = D.alphaMax; alphaPrimal[t] = alphaDualEq[t] = alphaDualIneq[t] = 0;
         norminf_grad[t] = norminf_eq[t] = gap[t] = ineq[t] = ineq1[t] = dual[t] = mp[t] = mn[t] = 0;
     }
@@ -91,6 +96,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     if (phase_first) {
     if (D.setAddEye2Hessian) {                                              // :150-155
         tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, run);
+        if (mm) tc_set_scalar(c, P, FN_setAddEye2HessianD, aeD, run);
         tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, run);
     }
     tc_copy(c, P, FN_initPrimal, run);                                      // :204
@@ -115,10 +121,10 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             aeU[t] = d[PS_aeU * S]; aeEq[t] = d[PS_aeEq * S]; mu[t] = d[PS_mu * S]; muMin[t] = d[PS_muMin * S];
             gapTol[t] = d[PS_gapTol * S]; alphaMax_[t] = d[PS_alphaMax * S]; alphaPrimal[t] = d[PS_alphaPrimal * S];
             alphaDualEq[t] = d[PS_alphaDualEq * S]; alphaDualIneq[t] = d[PS_alphaDualIneq * S];
-            mp[t] = d[PS_mp * S]; mn[t] = d[PS_mn * S];
+            mp[t] = d[PS_mp * S]; mn[t] = d[PS_mn * S]; aeD[t] = d[PS_aeD * S];
             iter[t] = q[PS_iter * S];
             const int fl = q[PS_flags * S];
-            run[t] = (fl & 1) != 0; updU[t] = (fl & 2) != 0; updEq[t] = (fl & 4) != 0;
+            run[t] = (fl & 1) != 0; updU[t] = (fl & 2) != 0; updEq[t] = (fl & 4) != 0; updD[t] = (fl & 8) != 0;
         }
     }
     tc_bT entered;
@@ -155,13 +161,54 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         }
         TC_FORT if (run[t] && norminf_grad[t] <= D.gradTolerance && (!hasF || gap[t] <= gapTol[t]) &&
                     (!hasG || norminf_eq[t] <= D.equalTolerance) &&
-                    (!adjust || aeU[t] <= D.addEye2HessianUtolerance)) {
+                    (!adjust || (aeU[t] <= D.addEye2HessianUtolerance && (!mm || aeD[t] <= D.addEye2HessianDtolerance)))) {
             status[t] = 0;
             run[t] = false;
         }
 
         // ---- regularisation control (:393-548) ----
-        if (adjust && eq) {                                                 // ipmPDeq_CSsolver.c:318-374
+        if (adjust && mm) {                                                 // ipmPDminmax_CSsolver.m:225-301
+            tc_bT prD;
+            TC_FORT { pr[t] = run[t] && updU[t]; prD[t] = run[t] && updD[t]; pr2[t] = run[t] && updEq[t]; }
+            tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);            // delayed from last iteration
+            tc_set_scalar(c, P, FN_setAddEye2HessianD, aeD, prD);
+            tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr2);
+            tc_bT retry;
+            TC_FORT { if (run[t]) updU[t] = updD[t] = updEq[t] = false; retry[t] = run[t]; }
+            for (int ii = 0; ii < 30 && tc_any_tile(retry); ii++) {
+                tc_get(c, P, FN_getDirectionError, retry);
+                tc_value(c, P, FN_getDirectionError, 0, retry, v0);         // derr
+                tc_get(c, P, FN_getHessDinertia, retry);
+                tc_value(c, P, FN_getHessDinertia, 1, retry, v1);           // mnD
+                tc_get(c, P, FN_getHessUinertia, retry);
+                tc_value(c, P, FN_getHessUinertia, 0, retry, v2);           // mpU
+                tc_bT nowU, nowD, nowEq;
+                TC_FORT {
+                    nowU[t] = nowD[t] = nowEq[t] = false;
+                    if (retry[t]) {
+                        const double derr = v0[t], mnD = v1[t], mpU = v2[t];
+                        if (mpU == D.mpUdesired && mnD == D.mnDdesired && derr <= 1e-7) {
+                            if (aeEq[t] > TC_addEye2HessianMIN) { aeEq[t] = TC_MAX(.75 * aeEq[t], TC_addEye2HessianMIN); updEq[t] = true; }
+                            if (aeU[t] > TC_addEye2HessianMIN) { aeU[t] = TC_MAX(.75 * aeU[t], TC_addEye2HessianMIN); updU[t] = true; }
+                            if (aeD[t] > TC_addEye2HessianMIN) { aeD[t] = TC_MAX(.75 * aeD[t], TC_addEye2HessianMIN); updD[t] = true; }
+                            retry[t] = false;                               // stored at the next iteration
+                        } else {
+                            // (:281,286 compare the update FLAG with the maximum, which always holds: restated as written)
+                            if (mpU < D.mpUdesired) { aeU[t] = TC_MIN(10 * aeU[t], TC_addEye2HessianUMAX); nowU[t] = true; }
+                            if (mnD < D.mnDdesired) { aeD[t] = TC_MIN(10 * aeD[t], TC_addEye2HessianUMAX); nowD[t] = true; }
+                            if (derr > 1e-7 && aeEq[t] < TC_addEye2HessianEqMAX) {
+                                aeEq[t] = TC_MIN(10 * aeEq[t], TC_addEye2HessianEqMAX);
+                                nowEq[t] = true;
+                            }
+                            if (!(nowU[t] || nowD[t] || nowEq[t])) retry[t] = false;
+                        }
+                    }
+                }
+                tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, nowU);      // immediate
+                tc_set_scalar(c, P, FN_setAddEye2HessianD, aeD, nowD);
+                tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, nowEq);
+            }
+        } else if (adjust && eq) {                                          // ipmPDeq_CSsolver.c:318-374
             TC_FORT { pr[t] = run[t] && updU[t]; pr2[t] = run[t] && updEq[t]; }
             tc_set_scalar(c, P, FN_setAddEye2HessianU, aeU, pr);
             tc_set_scalar(c, P, FN_setAddEye2HessianEq, aeEq, pr2);
@@ -412,7 +459,8 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
                 alphaDualIneq[t] = alphaPrimal[t];
             } else {
                 alphaDualIneq[t] *= TC_stepback;
-                if (alphaDualIneq[t] > alphaMax_[t]) alphaDualIneq[t] = alphaMax_[t];
+                const double cap = mm ? D.alphaMax : alphaMax_[t];           // min-max: obj.alphaMax (.m:399-401)
+                if (alphaDualIneq[t] > cap) alphaDualIneq[t] = cap;
                 alphaDualEq[t] = eq ? D.alphaMax : alphaDualIneq[t];         // eq :611
             }
         }
@@ -423,7 +471,22 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         // ---- barrier parameter update, skipAffine!=0 (:782-859) ----
         TC_FORT {
             bool set_mu = false, reinit_dual = false;
-            if (run[t] && D.skipAffine && eq) {                             // ipmPDeq_CSsolver.c:620-660
+            if (run[t] && mm) {                                             // ipmPDminmax_CSsolver.m:411-440
+                const bool th_grad = norminf_grad[t] <= TC_MAX(1e-3, 1e0 * D.gradTolerance);
+                const bool th_eq = !hasG || norminf_eq[t] <= TC_MAX(1e-5, 1e0 * D.equalTolerance);
+                if (alphaPrimal[t] > D.alphaMax / 2 && th_grad && th_eq) {
+                    const double a = D.muFactorAggressive * mu[t], b = mu[t] * sqrt(mu[t]);   // mu^1.5
+                    mu[t] = TC_MAX(muMin[t], TC_MIN(a, b));
+                    set_mu = true;
+                } else if (alphaPrimal[t] < .1) {
+                    mu[t] = TC_MIN(mu0, 1.1 * mu[t]);
+                    set_mu = true;
+                    reinit_dual = true;
+                } else if (alphaPrimal[t] > .99 && th_eq) {
+                    mu[t] = TC_MAX(mu[t] * D.muFactorConservative, muMin[t]);
+                    set_mu = true;
+                }
+            } else if (run[t] && D.skipAffine && eq) {                      // ipmPDeq_CSsolver.c:620-660
                 const bool th_grad = norminf_grad[t] < TC_MAX(1e-3, 1e0 * D.gradTolerance);
                 const bool th_eq = !hasG || norminf_eq[t] < TC_MAX(1e-5, 1e0 * D.equalTolerance);
                 if (alphaPrimal[t] > D.alphaMax / 2 && th_grad && th_eq) {
@@ -468,8 +531,8 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         TC_FORT {
             pr[t] = run[t] && alphaPrimal[t] < D.alphaMin && alphaDualIneq[t] < D.alphaMin &&
                     alphaDualEq[t] < D.alphaMin;
-            if (pr[t]) {                                                    // :853-859
-                mu[t] /= (D.muFactorConservative * D.muFactorConservative);
+            if (pr[t]) {                                                    // :853-859 (min-max: one division, .m:441-444)
+                mu[t] /= mm ? D.muFactorConservative : (D.muFactorConservative * D.muFactorConservative);
                 if (mu[t] < muMin[t]) mu[t] = muMin[t];
             }
         }
@@ -494,15 +557,17 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             TC_FORT if (diag[t]) {
                 if (v0[t] > gapTol[t]) status[t] |= 64;
                 if (mu[t] > muMin[t]) status[t] |= 128;
-                if (alphaPrimal[t] <= D.alphaMin && alphaDualIneq[t] < D.alphaMin && alphaDualEq[t] < D.alphaMin)
+                const double aI = alphaDualIneq[t], aE = alphaDualEq[t];
+                if (alphaPrimal[t] <= D.alphaMin && (mm ? aI <= D.alphaMin && aE <= D.alphaMin : aI < D.alphaMin && aE < D.alphaMin))
                     status[t] |= 1792;
-                else if (alphaPrimal[t] <= .1 && alphaDualIneq[t] < .1 && alphaDualEq[t] < .1)
+                else if (alphaPrimal[t] <= .1 && (mm ? aI <= .1 && aE <= .1 : aI < .1 && aE < .1))
                     status[t] |= 1536;
-                else if (alphaPrimal[t] <= .5 && alphaDualIneq[t] < .5 && alphaDualEq[t] < .5)
+                else if (alphaPrimal[t] <= .5 && (mm ? aI <= .5 && aE <= .5 : aI < .5 && aE < .5))
                     status[t] |= 1024;
             }
         }
-        TC_FORT if (adjust && !eq && diag[t] && aeU[t] > D.addEye2HessianUtolerance) status[t] |= 2048;
+        TC_FORT if (adjust && !eq && diag[t] &&
+                    (aeU[t] > D.addEye2HessianUtolerance || (mm && aeD[t] > D.addEye2HessianDtolerance))) status[t] |= 2048;
     }
     TC_FORT {
         status_out[t] = status[t];
@@ -517,9 +582,9 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
             d[PS_aeU * S] = aeU[t]; d[PS_aeEq * S] = aeEq[t]; d[PS_mu * S] = mu[t]; d[PS_muMin * S] = muMin[t];
             d[PS_gapTol * S] = gapTol[t]; d[PS_alphaMax * S] = alphaMax_[t]; d[PS_alphaPrimal * S] = alphaPrimal[t];
             d[PS_alphaDualEq * S] = alphaDualEq[t]; d[PS_alphaDualIneq * S] = alphaDualIneq[t];
-            d[PS_mp * S] = mp[t]; d[PS_mn * S] = mn[t];
+            d[PS_mp * S] = mp[t]; d[PS_mn * S] = mn[t]; d[PS_aeD * S] = aeD[t];
             q[PS_iter * S] = iter[t];
-            q[PS_flags * S] = (run[t] ? 1 : 0) | (updU[t] ? 2 : 0) | (updEq[t] ? 4 : 0);
+            q[PS_flags * S] = (run[t] ? 1 : 0) | (updU[t] ? 2 : 0) | (updEq[t] ? 4 : 0) | (updD[t] ? 8 : 0);
         }
     }
 }

@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include <vector_types.h>
 
-#define TC_MAGIC 0x3030324243540005LL
+#define TC_MAGIC 0x3030324243540006LL
 #define TC_CONST_BIT 0x40000000u   // io[] words (get/copy sources): constant-pool index
 #define TC_SLOT_MASK 0x3FFFFFFFu
 #define TC_NO_SLOT 0xFFFFFFFFu
@@ -45,6 +45,7 @@ enum tc_fn {
     FN_getHessInertia, FN_getMaxAlphas_s, FN_setAlphaPrimal, FN_getMinF_s, FN_setAlphaDualEq,
     FN_setAlphaDualIneq, FN_updatePrimalDual, FN_getJ, FN_getOutputs,
     FN_getMaxAlphas_a, FN_getMinF_a, FN_getRho,      // affine-scaling (Mehrotra) step, skipAffine=0 (ipmPD_CS.m:313-315,422-425)
+    FN_setAddEye2HessianD, FN_getHessDinertia, FN_getHessUinertia,   // min-max driver (ipmPDminmax_CS.m:181-192,266-272)
     FN_USER0
 };
 
@@ -69,7 +70,10 @@ struct tc_defines {         // the #define table of lib/cmex2optimizeCS.m:303-33
     int32_t nU, nG, nF;
     int32_t scaleCost, scaleInequalities, coupledAlphas, setAddEye2Hessian, adjustAddEye2Hessian,
         useInertia, skipAffine, delta;
-    int32_t driver;         // 0: ipmPD_CSsolver (lib/ipmPD_CSsolver.c), 1: ipmPDeq_CSsolver (lib/ipmPDeq_CSsolver.c)
+    int32_t driver;         // 0: ipmPD_CSsolver (lib/ipmPD_CSsolver.c), 1: ipmPDeq_CSsolver (lib/ipmPDeq_CSsolver.c),
+                            // 2: ipmPDminmax_CSsolver (lib/ipmPDminmax_CSsolver.m)
+    int32_t mpUdesired, mnDdesired, pad_;   // min-max: wanted inertia (ipmPDminmax_CSsolver.m:68-69)
+    double addEye2HessianDtolerance;
     double gradTolerance, addEye2HessianUtolerance, equalTolerance, desiredDualityGap, alphaMin,
         alphaMax, muFactorAggressive, muFactorConservative;
 };
@@ -105,8 +109,9 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     int32_t *ps_i;                // [TC_PS_NI][stride]
     int32_t *orig;                // [stride] original instance whose state lives in the column, -1: none
     int32_t *n_live;              // device scalar
+    double aeD0;                  // min-max driver: initial addEye2HessianD of this solve (addEye2Hessian[1])
 };
-#define TC_PS_ND 11
+#define TC_PS_ND 12
 #define TC_PS_NI 2
 
 // address of scratchbook slot `slot` of instance `inst`

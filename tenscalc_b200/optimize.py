@@ -302,3 +302,105 @@ def cmex2equilibriumLatentCS(*, classname: str, P1objective: Tcalculus, P2object
                     nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
                     n_groups=len(problem.groups), n_slots=problem.n_slots, driver="ipmPDeq_CSsolver")
     return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)
+
+
+# ------------------------------------------------------------------------------------------------
+# min-max problems: cmex2minmaxCS / class2minmaxCS -> ipmPDminmax_CSsolver
+# ------------------------------------------------------------------------------------------------
+def minmax_defines(nU: int, nD: int, nG: int, nF: int, nGd: int, nFd: int, *, gradTolerance: float = 1e-4,
+                   equalTolerance: float = 1e-4, desiredDualityGap: float = 1e-5, alphaMin: float = 1e-7,
+                   alphaMax: float = 1.0, coupledAlphas: bool = True, muFactorAggressive: float = .2,
+                   muFactorConservative: float = .95, scaleInequalities: bool = True, scaleCost: float = 0.0,
+                   addEye2Hessian: bool = True, adjustAddEye2Hessian: bool = False,
+                   addEye2HessianUtolerance: float = 1e-6, addEye2HessianDtolerance: float = 1e-6,
+                   solverVerboseLevel: int = 1, **ignored) -> Dict[str, object]:
+    """the properties the generated minmax class hands to its solver (lib/class2minmaxCS.m; defaults
+    lib/private/parameters4minmax.m, parameters4all.m)"""
+    return dict(
+        nZ=int(nU + nD), nU=int(nU), nD=int(nD), nG=int(nG), nF=int(nF),
+        mpUdesired=int(nU + nGd + nFd), mnDdesired=int(nD),       # ipmPDminmax_CSsolver.m:68-69
+        gradTolerance=float(gradTolerance), addEye2HessianUtolerance=float(addEye2HessianUtolerance),
+        addEye2HessianDtolerance=float(addEye2HessianDtolerance), equalTolerance=float(equalTolerance),
+        desiredDualityGap=float(desiredDualityGap), scaleCost=int(scaleCost != 0),
+        scaleInequalities=int(bool(scaleInequalities)), scaleEqualities=0, alphaMin=float(alphaMin),
+        alphaMax=float(alphaMax), coupledAlphas=int(bool(coupledAlphas)), setAddEye2Hessian=int(bool(addEye2Hessian)),
+        adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)), useInertia=1,
+        muFactorAggressive=float(muFactorAggressive), muFactorConservative=float(muFactorConservative), delta=3,
+        skipAffine=1, smallerNewtonMatrix=0, useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0, profiling=0,
+        verboseLevel=int(min(solverVerboseLevel, 1)), driver="ipmPDminmax_CSsolver")
+
+
+def cmex2minmaxCS(*, classname: str, objective: Tcalculus, minOptimizationVariables: Sequence[Tcalculus],
+                  maxOptimizationVariables: Sequence[Tcalculus], minConstraints: Sequence[Constraint] = (),
+                  maxConstraints: Sequence[Constraint] = (),
+                  outputExpressions: Union[Sequence[Tcalculus], Dict[str, Tcalculus]] = (),
+                  parameters: Sequence[Tcalculus] = (), ordering=None, **options) -> GeneratedSolver:
+    """``cmex2minmaxCS`` / ``class2minmaxCS`` (lib/cmex2minmaxCS.m, lib/class2minmaxCS.m): min over the first set of
+    variables of the max over the second; the generated class's ``solve`` runs ``ipmPDminmax_CSsolver``
+    (lib/ipmPDminmax_CSsolver.m -- the reference's C file of that name is stale, SURVEY.md Note A, so the MATLAB
+    solver is the specification and parity with it is UNPINNED: no oracle of the reference's own can be run here).
+    ``solve`` takes three regularisers ``addEye2Hessian=[U, D, Eq]``."""
+    from .ipm_builder_minmax import build_ipm_minmax
+    tab = T.table()
+    code = CSparse(tab)
+    if objective.numel() != 1:
+        raise ValueError("objective must be a scalar")
+    par_info = []
+    for p in parameters:
+        nm = _name_of(p)
+        code.declare_set(f"setP_{nm}", p.flat(), p.shape, kind="parameter")
+        par_info.append((nm, p.shape))
+    var_info = []
+
+    def pack(vars_):
+        ids, store = [], []
+        for v in vars_:
+            nm = _name_of(v)
+            e = v.flat()
+            st = [tab.new_set(f"{nm}_init[{k}]") for k in range(len(e))]
+            code.declare_set(f"setV_{nm}", st, v.shape, kind="variable")
+            ids += e
+            store += st
+            var_info.append((nm, v.shape))
+        return ids, store
+
+    u, u0 = pack(minOptimizationVariables)
+    d, d0 = pack(maxOptimizationVariables)
+    if len(set(u + d)) != len(u + d):
+        raise ValueError("optimisation variables must be distinct")
+    code.declare_copy("initPrimal__", u + d, u0 + d0)
+
+    def parse(cons):
+        Gs: List[Optional[int]] = []
+        Fs: List[Optional[int]] = []
+        for c in cons:
+            if not isinstance(c, Constraint):
+                raise ValueError("constraint is not a Tcalculus comparison")
+            (Gs if c.kind == "iszero" else Fs).extend(c.expr.flat())
+        return Gs, Fs
+
+    Gu, Fu = parse(minConstraints)
+    Gd, Fd = parse(maxConstraints)
+    mk = lambda nm, n: [tab.new_set(f"{nm}[{k}]") for k in range(n)]     # noqa: E731
+    nuU, lamU, nuD, lamD = mk("nuU_", len(Gu)), mk("lambdaU_", len(Fu)), mk("nuD_", len(Gd)), mk("lambdaD_", len(Fd))
+    keys = ("scaleInequalities", "scaleCost", "addEye2Hessian")
+    info = build_ipm_minmax(code, u, d, objective.e[()], Fu, Fd, Gu, Gd, lamU, lamD, nuU, nuD, ordering=ordering,
+                            **{k: options[k] for k in keys if k in options})
+    is_struct = isinstance(outputExpressions, dict)
+    items = list(outputExpressions.items()) if is_struct else [(f"y{k + 1}", e) for k, e in enumerate(outputExpressions)]
+    out_info, srcs, shapes, names = [], [], [], []
+    for nm, e in items:
+        e = Tcalculus._lift(e)
+        srcs.append(e.flat())
+        shapes.append(e.shape)
+        names.append(nm)
+        out_info.append((nm, e.shape))
+    code.declare_get("getOutputs", srcs, shapes, names)
+    defines = minmax_defines(len(u), len(d), info["nG"], info["nF"], info["nGd"], info["nFd"], **options)
+    problem = code.compile(defines)
+    fac = info["factor"]
+    from .ordering import DEFAULT as default_ordering
+    gen_info = dict(ordering=(ordering if isinstance(ordering, str) else "custom") if ordering is not None else default_ordering,
+                    nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
+                    n_groups=len(problem.groups), n_slots=problem.n_slots, driver="ipmPDminmax_CSsolver")
+    return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)

@@ -243,7 +243,37 @@ def qsaddle_latent(N: int = 20, **opts) -> Tuple[GeneratedSolver, dict]:
     return qsaddle(N, latent=True, **opts)
 
 
-BUILDERS = dict(sls=sls, l1l2=l1l2, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter, isa_probe=isa_probe,
+def minmax_box(N: int = 4, latent: bool = False, **opts) -> Tuple[GeneratedSolver, dict]:
+    """cases 5 and 5.5 of examples/minmaxTest.m:84-103, vectorised over N coordinates and with the offset as a
+    parameter: min_u max_d |u+d+a|^2 - 2|d+2|^2, -2<=u<=2, -1<=d<=1 (5.5: through x == u+d, x a maximiser variable);
+    class2minmaxCS options of the script (:106-118): addEye2Hessian, adjustAddEye2Hessian, no scaling"""
+    from .optimize import cmex2minmaxCS
+    T.clear()
+    u = Tvariable("u", N)
+    d = Tvariable("d", N)
+    a = Tvariable("a", N)
+    o = dict(scaleCost=0, addEye2Hessian=True, adjustAddEye2Hessian=True, scaleInequalities=False)
+    o.update(opts)
+    if latent:
+        x = Tvariable("x", N)
+        J = norm2(x) - 2 * norm2(d + 2)
+        gen = cmex2minmaxCS(classname="tmp_minmaxstate", objective=J, minOptimizationVariables=[u],
+                            maxOptimizationVariables=[d, x], minConstraints=[u >= -2, u <= 2],
+                            maxConstraints=[d >= -1, d <= 1, x == u + d + a], outputExpressions=dict(u=u, d=d, x=x, J=J),
+                            parameters=[a], **o)
+    else:
+        J = norm2(u + d + a) - 2 * norm2(d + 2)
+        gen = cmex2minmaxCS(classname="tmp_minmax", objective=J, minOptimizationVariables=[u],
+                            maxOptimizationVariables=[d], minConstraints=[u >= -2, u <= 2],
+                            maxConstraints=[d >= -1, d <= 1], outputExpressions=dict(u=u, d=d, J=J), parameters=[a], **o)
+    return gen, dict(mu0=1.0, maxIter=30, addEye2Hessian=(1e-9, 1e-9, 1e-9))
+
+
+def minmax_box_latent(N: int = 4, **opts) -> Tuple[GeneratedSolver, dict]:
+    return minmax_box(N, latent=True, **opts)
+
+
+BUILDERS = dict(sls=sls, l1l2=l1l2, minmax_box=minmax_box, minmax_box_latent=minmax_box_latent, mpc_dcmotor=mpc_dcmotor, mpc_quadcopter=mpc_quadcopter, isa_probe=isa_probe,
                 matrix_game=matrix_game, qsaddle=qsaddle, qsaddle_latent=qsaddle_latent)
 
 
@@ -326,6 +356,12 @@ def synthetic_inputs(name: str, gen: GeneratedSolver, batch: int, seed: int = 0)
         V = dict(u=u0, d=d0)
         if name == "qsaddle_latent":
             V["x"] = u0 + d0
+    elif name in ("minmax_box", "minmax_box_latent"):
+        N = dict(gen.parameters)["a"][0]
+        P = dict(a=rng.uniform(-1, 3, (N, B)))
+        V = dict(u=np.full((N, B), .1), d=np.full((N, B), .1))
+        if name == "minmax_box_latent":
+            V["x"] = V["u"] + V["d"] + P["a"]
     elif name == "isa_probe":
         N, n = dict(gen.parameters)["A"]
         P = dict(c=rng.uniform(.5, 1.5, (n, B)), A=rng.random((N, n, B)), b=rng.random((N, B)))

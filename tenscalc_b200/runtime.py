@@ -124,6 +124,14 @@ def _check(rc: int) -> None:
         raise TenscalcError(f"tenscalc_b200: {load_library().tc_error_string(rc).decode()} (code {rc})")
 
 
+def _regularisers(values):
+    """addEye2Hessian of solve(): {U, Eq} (ipmPD_CSsolver.c:139), {1, 2} (ipmPDeq_CSsolver) or, for min-max classes,
+    {U, D, Eq} (ipmPDminmax_CSsolver.m:46-60: missing entries repeat the last one)"""
+    v = [float(x) for x in values]
+    v += [v[-1]] * (3 - len(v))
+    return (ctypes.c_double * 3)(*v)
+
+
 class BatchedSolver:
     def __init__(self, gen: GeneratedSolver, batch: int, device: Optional[int] = None,
                  backend: str = "compiled", **module_opts):
@@ -208,7 +216,7 @@ class BatchedSolver:
         mu = ctypes.c_double(mu0)
         mi = ctypes.c_int32(maxIter)
         si = ctypes.c_int32(saveIter)
-        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        ae = _regularisers(addEye2Hessian)
         status = np.empty(self.batch, dtype=np.int32)
         it = np.empty(self.batch, dtype=np.int32)
         t = ctypes.c_double(0)
@@ -241,7 +249,7 @@ class BatchedSolver:
         mu = ctypes.c_double(mu0)
         mi = ctypes.c_int32(maxIter)
         si = ctypes.c_int32(saveIter)
-        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        ae = _regularisers(addEye2Hessian)
         _check(self._lib.tc_solve_device(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
                                          ctypes.c_void_p(status_ptr), ctypes.c_void_p(iter_ptr)))
 
@@ -251,7 +259,7 @@ class BatchedSolver:
         mu = ctypes.c_double(mu0)
         mi = ctypes.c_int32(maxIter)
         si = ctypes.c_int32(saveIter)
-        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        ae = _regularisers(addEye2Hessian)
         t = ctypes.c_double(0)
         _check(self._lib.tc_solve(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
                                   status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p),
@@ -265,7 +273,7 @@ class BatchedSolver:
         mu = ctypes.c_double(mu0)
         mi = ctypes.c_int32(maxIter)
         si = ctypes.c_int32(saveIter)
-        ae = (ctypes.c_double * 2)(*addEye2Hessian)
+        ae = _regularisers(addEye2Hessian)
         _check(self._lib.tc_solve_async(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
                                         status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p)))
 

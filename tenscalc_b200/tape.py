@@ -48,7 +48,7 @@ from . import itable as it
 from .csparse import CompiledProblem
 from .optimize import GeneratedSolver
 
-MAGIC = 0x3030324243540005  # "\x03\0TCB200" little-endian tag + format version
+MAGIC = 0x3030324243540006  # "\x03\0TCB200" little-endian tag + format version
 CONST_BIT = 1 << 30         # io[] words only (get/copy sources): constant-pool index
 NO_SLOT = 0xFFFFFFFF
 
@@ -83,12 +83,13 @@ FN = {name: k for k, name in enumerate([
     "getNorminf_G__", "getGapMinFMinLambda__", "getCurvature__", "getDirectionError__",
     "getHessInertia__", "getMaxAlphas_s__", "setAlphaPrimal__", "getMinF_s__", "setAlphaDualEq__",
     "setAlphaDualIneq__", "updatePrimalDual__", "getJ__", "getOutputs",
-    "getMaxAlphas_a__", "getMinF_a__", "getRho__"])}
+    "getMaxAlphas_a__", "getMinF_a__", "getRho__",
+    "setAddEye2HessianD__", "getHessDinertia__", "getHessUinertia__"])}
 FN_USER0 = len(FN)
 # the equilibrium driver (lib/ipmPDeq_CSsolver.c:28-52) calls three of the slots by other names
 EQ_NAMES = {"setAddEye2HessianU__": "setAddEye2Hessian1__", "setAddEye2HessianEq__": "setAddEye2Hessian2__",
             "initDualEqX__": "initDualEq__"}
-DRIVERS = {"ipmPD_CSsolver": 0, "ipmPDeq_CSsolver": 1}
+DRIVERS = {"ipmPD_CSsolver": 0, "ipmPDeq_CSsolver": 1, "ipmPDminmax_CSsolver": 2}
 
 
 def driver_of(pr: CompiledProblem) -> str:
@@ -413,11 +414,14 @@ def serialize(gen: GeneratedSolver) -> bytes:
     ih[19:27] = (d["scaleCost"], d["scaleInequalities"], d["coupledAlphas"], d["setAddEye2Hessian"],
                  d["adjustAddEye2Hessian"], d["useInertia"], d["skipAffine"], d["delta"])
     ih[27] = DRIVERS[str(d.get("driver", "ipmPD_CSsolver"))]
-    if ih[27] == 1:
+    if ih[27] in (1, 2):
         ih[16] = d["nZ"]          # the device driver only tests nG > 0 / nF > 0 and divides by nF
+    if ih[27] == 2:
+        ih[28:30] = (d["mpUdesired"], d["mnDdesired"])
     dh = np.zeros(16, dtype=np.float64)
     dh[0:8] = (d["gradTolerance"], d["addEye2HessianUtolerance"], d["equalTolerance"], d["desiredDualityGap"],
                d["alphaMin"], d["alphaMax"], d["muFactorAggressive"], d["muFactorConservative"])
+    dh[8] = d.get("addEye2HessianDtolerance", 0.0)
 
     def pad16(b: bytes) -> bytes:
         return b + b"\0" * (-len(b) % 16)

@@ -28,7 +28,10 @@ CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_qu
          ("matrix_game", 512, {}), ("qsaddle", 512, {}), ("qsaddle_latent", 512, {}),
          ("qsaddle", 256, {"useLDL": True}),                                  # normal equations + LDL' (ipmPDeqlat_CS.m:645-651)
          ("matrix_game", 256, {"skipAffine": False}),
-         ("qsaddle", 256, {"addEye2Hessian": True, "adjustAddEye2Hessian": True})]     # regulariser retries (:318-374)                         # affine-scaling step of the eq driver (:326-398)
+         ("qsaddle", 256, {"addEye2Hessian": True, "adjustAddEye2Hessian": True}),     # regulariser retries (:318-374)
+         # min-max: cmex2minmaxCS -> ipmPDminmax_CSsolver (three regularisers, inertia control).  PARITY UNPINNED:
+         # the oracle's driver is a C transcription of the reference's MATLAB solver (oracle/ipm_driver_minmax_port.c)
+         ("minmax_box", 512, {}), ("minmax_box_latent", 512, {}), ("minmax_box", 256, {"N": 16})]                         # affine-scaling step of the eq driver (:326-398)
 
 
 def _oracle(gen, name):

@@ -33,7 +33,7 @@ def _run(oracle, gen, g):
     B = g["P"].shape[0]
     nY = sum(int(np.prod(s)) if s else 1 for _, s in gen.outputs)
     Y = np.zeros((B, nY)); st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); sec = np.zeros(B)
-    ae = np.array([1e-9, 1e-9])
+    ae = np.array([1e-9, 1e-9, 1e-9])
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
     P, V = np.ascontiguousarray(g["P"]), np.ascontiguousarray(g["V"])
     lib.oracle_run_batch(B, P.ctypes.data_as(dp), V.ctypes.data_as(dp), float(g["mu0"]), int(g["maxIter"]), -1,
@@ -97,6 +97,20 @@ def test_equilibrium_solutions_are_saddle_points():
     Ad = np.einsum("ijb,jb->ib", A, d)                           # P1 minimises: no row does better than the value
     uA = np.einsum("ib,ijb->jb", u, A)                           # P2 maximises: no column does better
     assert (Ad.min(0) > v - 1e-3).all() and (uA.max(0) < v + 1e-3).all()
+
+
+def test_minmax_port_solves_the_box_game():
+    """ipmPDminmax_CSsolver (PARITY UNPINNED, oracle/ipm_driver_minmax_port.c) on cases 5 / 5.5 of
+    examples/minmaxTest.m: min_u max_d |u+d+a|^2-2|d+2|^2 on -2<=u<=2, -1<=d<=1 has d=-1, u=clip(1-a,-2,2)"""
+    from oracle.oracle import Oracle
+    for name in ("minmax_box", "minmax_box_latent"):
+        gen, args = generated(name)
+        P, V = problems.synthetic_inputs(name, gen, 32, seed=3)
+        st, it, out, _ = Oracle(gen, "port").solve_batch(P, V, args["mu0"], args["maxIter"], addEye2Hessian=args["addEye2Hessian"])
+        assert (st == 0).all() and it.max() <= 20
+        assert np.abs(out["d"] + 1).max() < 1e-5
+        assert np.abs(out["u"] - np.clip(1 - P["a"], -2, 2)).max() < 2e-3        # interior-point accuracy next to an active bound
+        assert np.abs(out["J"] + 2 * P["a"].shape[0] - ((np.clip(1 - P["a"], -2, 2) - 1 + P["a"]) ** 2).sum(0)).max() < 2e-3
 
 
 def test_golden_status_zero_on_examples():

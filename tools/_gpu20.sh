@@ -1,0 +1,9 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 6 --warmup 3 --no-cpu > gpurun_out/r02x_bench_quadcopter_2gpu.json 2> gpurun_out/r02x_2gpu.err
+tail -2 gpurun_out/r02x_2gpu.err | cut -c1-300
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r02x_bench_quadcopter_2gpu.json"))
+print("2gpu value",d["value"],"ms/step",d["ms_per_step"],"e2e",d["e2e"],"strong",d.get("strong_scaling"),"per_rank",d["per_rank"]["total_ms"])
+PY
