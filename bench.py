@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per core in the CPU baseline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=5,
+    ap.add_argument("--pipeline", type=int, default=7,
                     help="solver handles kept in flight (own stream + scratchbook each): the straggler tail of "
                          "step k overlaps the bulk of steps k+1.. ; 1 = strictly one batch at a time")
     ap.add_argument("--driver", default="", choices=["", "warp", "lanes"],

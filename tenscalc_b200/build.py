@@ -87,16 +87,20 @@ def _toolchain_tag(emit_opts: dict) -> str:
 
 def default_module_opts(gen, **given) -> dict:
     """launch shape per problem size (measured on B200, profiles/): small scratchbooks (mpc_dcmotor,
-    sls) run fastest with many light warps -- 24 warps/SM at 80 registers, 28 operands per chunk.  Large
-    ones (mpc_quadcopter, l1l2) run 12 warps/SM at 168 registers with 72 operands per chunk, the warps
-    grouped in CTAs of 4 that walk the straight-line code in lockstep (one barrier per chunk), so that the
-    instruction stream -- the largest stall of these kernels is instruction fetch -- is fetched once per
-    CTA: +17 % over 8 independent warps/SM at 255 registers (profiles/r02i_*).  Lockstep needs the
+    sls) run fastest with many light warps -- 24 warps/SM at 80 registers, 28 operands per chunk, the
+    next chunk's operands prefetched into L2.  Large ones (mpc_quadcopter, l1l2) run 12 warps/SM at 168
+    registers with 72 operands per chunk, the warps grouped in CTAs of 4 that walk the straight-line
+    code in lockstep (one barrier per chunk), so that the instruction stream -- instruction fetch is a
+    fifth of these kernels' time, half of the lines that miss the SM come from DRAM -- is fetched once
+    per CTA: +17 % over 8 independent warps/SM at 255 registers (profiles/r02i_*); and WITHOUT the L2
+    prefetch: the bulk phases are DRAM-throughput bound (4.2-4.4 TB/s of 256-byte segments), so the
+    prefetch instructions (one per operand, 14 % of all instructions) only cost issue slots -- +10 % on
+    mpc_quadcopter and l1l2 without them (profiles/r03_experiments.md).  Lockstep needs the
     warp-synchronous driver with one instance per lane."""
     solo = given.get("driver", "warp") != "warp" or given.get("tiles", 1) != 1
     if gen.problem.n_slots <= 8192:        # lockstep 8: mpc_dcmotor +13 %, sls +7 % (profiles/r02j_*)
         return dict(warps_per_sm=24, max_loads=28, **({} if solo else dict(lockstep=8)))
-    return {} if solo else dict(lockstep=4, warps_per_sm=12, max_loads=72)
+    return dict(prefetch=0) if solo else dict(lockstep=4, warps_per_sm=12, max_loads=72, prefetch=0)
 
 
 def module_path(gen, **emit_opts) -> str:

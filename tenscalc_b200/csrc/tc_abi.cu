@@ -284,7 +284,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     if (!s) return TC_EINVAL;
     s->device = device;
     s->batch = batch;
-    s->stride = (batch + 255) / 256 * 256;   // whole CTAs for every back end (TC_BLOCK, 32*TC_LOCKSTEP <= 256)
+    s->stride = (batch + 767) / 768 * 768;   // whole CTAs for every back end (TC_BLOCK = 256; 32*TC_LOCKSTEP divides 768)
     const int64_t n_slots = ih[1], n_groups = ih[2], n_funcs = ih[3], n_sets = ih[4], n_out = ih[5],
                   tape_cells = ih[6], n_consts = ih[7], io_words = ih[8], n_persist = ih[11];
     s->n_slots = n_slots;
@@ -462,6 +462,7 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
     auto load = (int (*)(void))dlsym(h, "tcm_load");
     auto work = (int (*)(void))dlsym(h, "tcm_work_tiles");   // > 0: work-queue driver, resident warps
     auto phs = (int (*)(void))dlsym(h, "tcm_phased");        // 1: the module's driver can run a solve in phases
+    auto ilv = (int (*)(void))dlsym(h, "tcm_interleave");    // 1: the two instances of a lane are interleaved (pair)
     if (!load || !abi || !img || !blk || !fp || !solve || !eval || abi() != TCM_ABI || img() != (int)sizeof(tc_device_image) ||
         blk() <= 0 || s->stride % blk() || (fingerprint && strcmp(fingerprint, fp()))) {
         dlclose(h);
@@ -494,10 +495,13 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
         }
     }
     s->module = h;
+    s->img.ilv = ilv ? ilv() : 0;   // scratchbook layout of the module; nothing has been written yet (tc_create + attach)
     s->mod_solve = solve;
     s->mod_eval = eval;
     s->mod_phased = phs ? phs() : 0;
-    fprintf(stderr, "tenscalc_b200: module %s attached (%s)\n", path, s->mod_phased && s->phased ? "phased solve" : "single-launch solve");
+    auto occ = (int (*)())dlsym(h, "tcm_occupancy");
+    fprintf(stderr, "tenscalc_b200: module %s attached (%s, %d CTAs of %d instances per SM)\n", path,
+            s->mod_phased && s->phased ? "phased solve" : "single-launch solve", occ ? occ() : -1, blk());
     // Warm-up launch over an EMPTY batch (one CTA, every lane invalid: nothing is read or written but
     // the lanes' own group-status words): the first launch of a module makes the driver size the
     // local-memory pool for the kernel's stack frames, 0.1-0.3 s that would otherwise be charged to the

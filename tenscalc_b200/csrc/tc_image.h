@@ -110,10 +110,16 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     int32_t *orig;                // [stride] original instance whose state lives in the column, -1: none
     int32_t *n_live;              // device scalar
     double aeD0;                  // min-max driver: initial addEye2HessianD of this solve (addEye2Hessian[1])
+    // log2 of the instances a lane carries INTERLEAVED (emitter option pair): 0: m[tile][slot][lane];
+    // 1: m[tile pair][slot][lane][2] -- the two instances of a lane sit side by side, so one 128-bit access
+    // moves slot s of both (set by tc_attach_module from the module, before anything is written)
+    int32_t ilv;
+    int32_t pad2_;
 };
 #define TC_PS_ND 12
 #define TC_PS_NI 2
 
 // address of scratchbook slot `slot` of instance `inst`
-#define TC_M(P, slot, inst) \
-    ((P).m[((size_t)((inst) >> 5) * (size_t)(P).n_slots + (size_t)(slot)) * TC_TILE + ((inst) & 31)])
+#define TC_M(P, slot, inst)                                                                                   \
+    ((P).m[(((size_t)((inst) >> (5 + (P).ilv)) * (size_t)(P).n_slots + (size_t)(slot)) * TC_TILE << (P).ilv) + \
+           ((size_t)((inst) & 31) << (P).ilv) + (((inst) >> 5) & ((1 << (P).ilv) - 1))])

@@ -42,6 +42,13 @@
 #ifndef TC_TILES
 #define TC_TILES 1         // instances per lane = scratchbook tiles per warp (compiled back end: emit_cuda.py)
 #endif
+// doubles between two slots of one instance: 32, or 64 when the two instances of a lane are interleaved
+// (emitter option pair, tc_device_image::ilv = 1)
+#ifdef TC_PAIR
+#define TC_SLOT_STRIDE (2 * TC_TILE)
+#else
+#define TC_SLOT_STRIDE TC_TILE
+#endif
 
 struct tc_lane {
     double *mb[TC_TILES];  // &m[tile][0][lane]; slot k of the instance in tile t is mb[t][k*32]
@@ -250,7 +257,7 @@ __device__ __forceinline__ void tc_exec_group(tc_lane &c, const uint32_t *group_
 __device__ __forceinline__ double tc_ldop(const tc_lane &c, int t, uint32_t w, bool pred) {
     const uint32_t idx = w & TC_SLOT_MASK;
     if (w & TC_CONST_BIT) return __ldg(c.consts + idx);                 // warp-uniform branch
-    return pred ? c.mb[t][(size_t)idx * TC_TILE] : 0.0;
+    return pred ? c.mb[t][(size_t)idx * TC_SLOT_STRIDE] : 0.0;
 }
 
 __device__ __forceinline__ void tc_run_parents(tc_lane &c, const tc_device_image &P, const tc_func *f,
@@ -300,7 +307,7 @@ __device__ __forceinline__ void tc_set_scalar(tc_lane &c, const tc_device_image 
     uint32_t slot = __ldg(P.io + f->io_off);
 #pragma unroll
     for (int t = 0; t < TC_TILES; t++)
-        if (pred[t]) c.mb[t][(size_t)slot * TC_TILE] = value[t];
+        if (pred[t]) c.mb[t][(size_t)slot * TC_SLOT_STRIDE] = value[t];
     tc_invalidate(c, f, pred);
 }
 
@@ -338,7 +345,7 @@ __device__ __noinline__ void tc_copy(tc_lane &c, const tc_device_image &P, int f
 #pragma unroll
         for (int t = 0; t < TC_TILES; t++) {
             double v = tc_ldop(c, t, s, pred[t]);
-            if (pred[t]) c.mb[t][(size_t)d * TC_TILE] = v;
+            if (pred[t]) c.mb[t][(size_t)d * TC_SLOT_STRIDE] = v;
         }
     }
     tc_invalidate(c, f, pred);

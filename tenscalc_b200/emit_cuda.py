@@ -147,14 +147,81 @@ def chunk_group(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_
     return chunks
 
 
+def plan_scache(reads: List[List[int]], makes: List[List[int]], ext: Set[int], capacity: int):
+    """Offline allocation of a per-lane shared-memory cache of ``capacity`` doubles for one group.
+
+    The access trace of a group is static, so the replacement policy can be the optimal one (Belady:
+    after every chunk keep the ``capacity`` values whose next use is nearest) and every decision is taken
+    here, at generation time: the emitted code holds plain shared-memory reads and writes at fixed
+    slots, no tags, no lookups.  ``reads[k]`` are the distinct scratchbook operands chunk k takes from
+    outside itself, ``makes[k]`` the values it produces.  Returns per chunk
+    ``(from_smem {value: slot}, to_smem [(value, slot)])`` and the set of produced values that must
+    ALSO be stored in the scratchbook (read outside the group, or dropped from the cache before their
+    last use); a produced value that stays cached until its last use never touches HBM."""
+    INF = 1 << 60
+    uses: Dict[int, List[int]] = {}
+    for k, rs in enumerate(reads):
+        for q in rs:
+            uses.setdefault(q, []).append(k)
+    ptr: Dict[int, int] = {}
+
+    def next_use(q: int, k: int) -> int:
+        u = uses.get(q)
+        if not u:
+            return INF
+        p = ptr.get(q, 0)
+        while p < len(u) and u[p] <= k:
+            p += 1
+        ptr[q] = p
+        return u[p] if p < len(u) else INF
+
+    cache: Dict[int, int] = {}             # value -> slot
+    free = list(range(capacity - 1, -1, -1))
+    plan = []
+    to_hbm: Set[int] = set()
+    made_all = {i for ms in makes for i in ms}
+    for k, (rs, ms) in enumerate(zip(reads, makes)):
+        from_smem = {q: cache[q] for q in rs if q in cache}
+        cand = [(next_use(q, k), n, q) for n, q in enumerate(list(cache) + [q for q in rs if q not in cache] + list(ms))]
+        cand = sorted(c for c in cand if c[0] < INF)
+        keep = {q for _, _, q in cand[:capacity]}
+        for q in [q for q in cache if q not in keep]:
+            free.append(cache.pop(q))
+        for _, _, q in cand[capacity:]:
+            if q in made_all:              # leaves (or never enters) the cache with uses ahead: needs its HBM copy
+                to_hbm.add(q)
+        to_smem = []
+        for _, _, q in cand[:capacity]:
+            if q not in cache:
+                cache[q] = free.pop()
+                to_smem.append((q, cache[q]))
+        plan.append((from_smem, to_smem))
+    to_hbm |= made_all & ext
+    return plan, to_hbm
+
+
 def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                max_loads: int = 96, prefetch: int = 1, merge: int = 1,
-               assume_global: int = 0, barrier: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
-    """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics"""
+               assume_global: int = 0, barrier: int = 0, scache: int = 0,
+               pair: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+    """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics.
+
+    ``pair``: every lane carries TWO instances whose scratchbook columns are interleaved
+    (``m[tile pair][slot][lane][2]``): a chunk runs the group on both -- one 128-bit load or store
+    moves slot s of both instances, the arithmetic is emitted twice (two independent dependency
+    chains per lane).  The chunk runs on both instances whenever either needs the group:
+    re-evaluating a group on unchanged inputs rewrites the same values, evaluating one whose inputs
+    are stale only touches values that are recomputed before anybody reads them (the caller marks
+    the group valid only for the instances that asked)."""
+    W = 2 if pair else 1           # doubles per lane and slot
+    ty = "double2" if pair else "double"
+    insts = ("x", "y") if pair else ("",)
     tab, slot = pr.tab, pr.slot
     members = pr.groups[g]
     chunks = chunk_group(pr, members, max_refs, max_loads)
     chunk_of = {i: k for k, ch in enumerate(chunks) for i in ch}
+    const_types = (it.I_load, it.I_2)
+    skip_types = (it.I_set, it.I_load, it.I_2)
     # results read by a later chunk of the same group
     cross: Set[int] = set()
     for i in members:
@@ -162,44 +229,85 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             k = chunk_of.get(o)
             if k is not None and k != chunk_of[i]:
                 cross.add(o)
-    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0)
-    bodies = []                    # per chunk: (name, load slots in issue order, store slots, statements)
+    # per chunk: the distinct scratchbook operands it takes from outside itself (in order of first use) and
+    # the values it produces
+    reads: List[List[int]] = []
+    makes: List[List[int]] = []
+    for ch in chunks:
+        have: Set[int] = set()
+        rs: List[int] = []
+        ms: List[int] = []
+        for i in ch:
+            if tab.types[i] in skip_types:
+                continue
+            for q in tab.operands[i]:
+                if tab.types[q] not in const_types and q not in have:
+                    have.add(q)
+                    rs.append(q)
+            have.add(i)
+            ms.append(i)
+        reads.append(rs)
+        makes.append(ms)
+    if scache:
+        plan, to_hbm = plan_scache(reads, makes, ext, scache)
+    else:
+        plan, to_hbm = [({}, []) for _ in chunks], ext | cross
+    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0, smem_loads=0, smem_stores=0)
+    bodies = []                    # per chunk: (name, HBM load slots in issue order, store slots, statements)
+    def ld(q: int, e: str) -> str:          # a fetched operand of instance e: the vector's component
+        return f"v{q}.{e}" if pair else f"v{q}"
+
+    def made(q: int, e: str) -> str:        # a result of instance e
+        return f"v{q}{e}"
+
     for k, ch in enumerate(chunks):
         name = f"tcg{g}_{k}"
-        loads: List[int] = []      # every scratchbook operand of the chunk, issued back to back up front:
-        lines: List[str] = []      # one memory round trip per chunk instead of one per use
+        from_smem, to_smem = plan[k]
+        keep_slot = dict(to_smem)
+        fetched = set(reads[k])
+        # every operand of the chunk is fetched up front, back to back: one memory round trip per chunk instead of
+        # one per use (the scratchbook loads first, then the shared-memory cache hits)
+        if pair:
+            head = [f"const double2 v{q}=*(const double2 *)(sc+{from_smem[q] * TILE * W});" for q in reads[k] if q in from_smem]
+        else:
+            head = [f"const double v{q}=sc[{from_smem[q] * TILE}];" for q in reads[k] if q in from_smem]
+        loads = [q for q in reads[k] if q not in from_smem]
+        lines: List[str] = []
+        tail: List[str] = []       # loaded operands that enter the cache: written at the end, when they have arrived
         stores: Set[int] = set()
-        have: Set[int] = set()
+        stats["loads"] += len(loads)
+        stats["smem_loads"] += len(head)
+        for q in loads:
+            if q in keep_slot:
+                tail.append(f"*(double2 *)(sc+{keep_slot[q] * TILE * W})=v{q};" if pair else f"sc[{keep_slot[q] * TILE}]=v{q};")
+                stats["smem_stores"] += 1
         for i in ch:
             t, p = tab.types[i], tab.params[i]
-            if t == it.I_set:
+            if t in skip_types:               # constants are immediates at their uses (gets/copies read the pool)
                 continue
-            if t in (it.I_load, it.I_2):      # constants are immediates at their uses (gets/copies read the pool)
-                continue
-            o: List[str] = []
-            for q in tab.operands[i]:
-                tq = tab.types[q]
-                if tq == it.I_load:
-                    o.append("(" + _lit(tab.params[q][0]) + ")")
-                elif tq == it.I_2:
-                    o.append("2.0")
-                else:
-                    if q not in have:
-                        loads.append(q)
-                        have.add(q)
-                        stats["loads"] += 1
+            for e in insts:
+                o: List[str] = []
+                for q in tab.operands[i]:
+                    tq = tab.types[q]
+                    if tq == it.I_load:
+                        o.append("(" + _lit(tab.params[q][0]) + ")")
+                    elif tq == it.I_2:
+                        o.append("2.0")
                     else:
-                        stats["reg_reads"] += 1
-                    o.append(f"v{q}")
-            lines.append(expression(t, p, o, f"v{i}"))
-            have.add(i)
-            if i in ext or i in cross:
-                lines.append(f"mt[{int(slot[i]) * TILE}]=v{i};")
+                        o.append(ld(q, e) if q in fetched else made(q, e))
+                lines.append(expression(t, p, o, made(i, e)))
+            stats["reg_reads"] += len(tab.operands[i])
+            both = f"make_double2(v{i}x,v{i}y)" if pair else f"v{i}"
+            if i in keep_slot:
+                lines.append(f"*(double2 *)(sc+{keep_slot[i] * TILE * W})={both};" if pair else f"sc[{keep_slot[i] * TILE}]={both};")
+                stats["smem_stores"] += 1
+            if i in to_hbm:
+                lines.append(f"*(double2 *)(mt+{int(slot[i]) * TILE * W})={both};" if pair else f"mt[{int(slot[i]) * TILE}]={both};")
                 stores.add(int(slot[i]))
                 stats["stores"] += 1
-            else:
+            elif i not in keep_slot:
                 stats["reg_only"] += 1
-        bodies.append((name, loads, stores, lines))
+        bodies.append((name, loads, stores, head, lines + tail))
     out: List[Tuple[str, str]] = []
     # `merge` consecutive chunks share one function (each chunk in its own scope): the ABI's
     # callee-saved register spill/restore is paid once per function instead of once per chunk
@@ -208,15 +316,25 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
         src = [f"__device__ __noinline__ void {fname}(double *__restrict__ m, unsigned mask) {{"]
         if assume_global:          # LDG/STG instead of generic LD/ST (the pointer's address space is not
             src.append("__builtin_assume(__isGlobal(m));")   # visible across -rdc translation units)
+        if scache:                 # the lane's column of its warp's cache: [slot][lane], conflict-free
+            src.append("double *__restrict__ sc = TC_SCACHE;")   # (pair: 16 bytes per lane and slot)
         for k in range(f0, min(f0 + merge, len(bodies))):
-            name, loads, stores, lines = bodies[k]
+            name, loads, stores, head, lines = bodies[k]
             # one pass over the chunk's code per tile of the warp: the second pass runs out of the
             # instruction cache (TC_TILE_LOOP / TC_MT are defined in the module header)
-            if barrier:            # lockstep: the warps of the CTA enter every chunk together, so its code is
-                src.append("__syncthreads();")   # fetched once per CTA while it is still in the instruction caches
-            src.append("TC_TILE_LOOP {")
-            src.append("double *__restrict__ mt = TC_MT;")
-            src += [f"const double v{q}=mt[{int(slot[q]) * TILE}];" for q in loads]
+            # lockstep: the warps of the CTA enter every chunk together, so its code is fetched once per CTA while
+            # it is still in the instruction caches.  (Every barrier ends a basic block and ptxas re-creates the
+            # uniform registers of the memory descriptors in each -- ~0.5 R2UR per load; a barrier every 4th
+            # chunk halves them and measures the same, profiles/r03_experiments.md.)
+            if barrier:
+                src.append("__syncthreads();")
+            src.append("if (mask) {" if pair else "TC_TILE_LOOP {")
+            src.append("double *__restrict__ mt = m;" if pair else "double *__restrict__ mt = TC_MT;")
+            if pair:
+                src += [f"const double2 v{q}=*(const double2 *)(mt+{int(slot[q]) * TILE * W});" for q in loads]
+            else:
+                src += [f"const double v{q}=mt[{int(slot[q]) * TILE}];" for q in loads]
+            src += head
             # while this chunk's operands are in flight, pull the operands of the chunk `prefetch` positions ahead
             # into L2: its load phase then costs an L2 hit instead of an HBM round trip (no registers involved);
             # with a distance above 1 the first chunks of the group also cover the chunks in between
@@ -231,7 +349,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                     nxt += [int(slot[q]) for q in bodies[kt][1] if int(slot[q]) not in mine and int(slot[q]) not in between]
             if nxt:                # the clobber keeps this chunk's own loads ahead of the prefetches
                 src.append('asm volatile("" ::: "memory");')
-                src += [f"TC_PREFETCH(mt+{sl * TILE});" for sl in dict.fromkeys(nxt)]
+                src += [f"TC_PREFETCH(mt+{sl * TILE * W});" for sl in dict.fromkeys(nxt)]
                 stats["prefetches"] += len(set(nxt))
             src += lines
             src.append("}")
@@ -247,7 +365,7 @@ EMITTER_VERSION = 1
 TCM_ABI = 2
 
 
-def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) -> List[Tuple[str, str]]:
+def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, pair: int = 0) -> List[Tuple[str, str]]:
     """chunks of one copy function: sequential ``m[d]=m[s]`` (writeCfunctionpergroup.m:753-852)"""
     tab, slot = pr.tab, pr.slot
     c = pr.copies[name]
@@ -263,8 +381,8 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
             elif ts == it.I_2:
                 src = "2.0"
             else:
-                src = f"mt[{int(slot[s]) * TILE}]"
-            lines.append(f"mt[{int(slot[d]) * TILE}]={src};")
+                src = f"mt[{int(slot[s]) * TILE * (2 if pair else 1)}]"
+            lines.append(f"mt[{int(slot[d]) * TILE * (2 if pair else 1)}]={src};")
         lines += ["}", "}"]
         out.append((f"tcc{fn_id}_{k // max_pairs}", "\n".join(lines) + "\n"))
     return out
@@ -272,7 +390,8 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192) 
 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
                 warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1,
-                assume_global: int = 0, resident: int = 0, driver: str = "warp"):
+                assume_global: int = 0, resident: int = 0, driver: str = "warp", scache: int = 0,
+                pair: int = 0):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
     from .csparse import fingerprint
     from .tape import FN
@@ -280,10 +399,15 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     ext = external_values(pr)
     funcs: List[Tuple[str, str]] = []
     group_calls: List[List[str]] = []
-    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0)
+    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0, smem_loads=0, smem_stores=0)
     per_group = []
+    if scache and ((tiles != 1 and not pair) or resident or driver != "warp"):
+        raise ValueError("scache needs the warp driver with one instance per lane (or pair) and no `resident` cap")
+    if scache * 8 * TILE * lockstep * (2 if pair else 1) > 227 * 1024:
+        raise ValueError("scache: more than 227 KB of shared memory per CTA")
     for g in range(len(pr.groups)):
-        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global, barrier=int(lockstep > 1))
+        fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global,
+                            barrier=int(lockstep > 1), scache=scache, pair=pair)
         funcs += fs
         group_calls.append([n for n, _ in fs])
         per_group.append(st)
@@ -295,19 +419,34 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         raise ValueError("the lane-decoupled and work-queue drivers implement ipmPD_CSsolver only")
     for name, fid in fn_items(pr):
         if name in pr.copies:
-            fs = emit_copy(pr, fid, name)
+            fs = emit_copy(pr, fid, name, pair=pair)
             funcs += fs
             copy_calls[fid] = [n for n, _ in fs]
     # part files of roughly equal size (ptxas time is what we balance)
+    if pair:                       # two interleaved instances per lane: the driver's tiles machinery with the
+        if tiles not in (1, 2) or driver != "warp":     # pair layout (TC_PAIR) and 128-bit accesses
+            raise ValueError("pair needs the warp driver (and implies tiles=2)")
+        tiles = 2
     if tiles not in (1, 2, 4, 8):
         raise ValueError("tiles must be 1, 2, 4 or 8 instances per lane")
     head = ("// generated by tenscalc_b200/emit_cuda.py -- do not edit\n#include <cfloat>\n#include <cmath>\n#include \"tc_math.cuh\"\n"
             f"#define TC_TILES {tiles}\n#define TC_TILE_STRIDE {int(pr.n_slots) * TILE}ull\n"
+            + ("// pair: the lane's two instances are interleaved, m[tile pair][slot][lane][2] (tc_image.h, ilv = 1)\n"
+               "#define TC_PAIR 1\n"
+               '#define TC_TILE_LOOP _Pragma("unroll 1") for (int t = 0; t < 2; t++) if ((mask >> t) & 1u)\n'
+               "#define TC_MT (m + t)\n#if 0\n" if pair else "") +
             "#if TC_TILES > 1\n"
             '#define TC_TILE_LOOP _Pragma("unroll 1") for (int t = 0; t < TC_TILES; t++) if ((mask >> t) & 1u)\n'
             "#define TC_MT (m + (size_t)t * TC_TILE_STRIDE)\n"
             "#else\n#define TC_TILE_LOOP if (mask)\n#define TC_MT m\n#endif\n"
+            + ("#endif\n" if pair else "") +
             '#define TC_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))\n'
+            "// per-lane software cache in shared memory (emitter option scache, plan_scache): warp w of the CTA owns\n"
+            "// TC_SCACHE_SLOTS rows of 32 doubles, slot s of a lane is sc[32*s]\n"
+            f"#define TC_SCACHE_SLOTS {scache * (2 if pair else 1)}\n"
+            "extern __shared__ double tc_scache[];\n"
+            "#define TC_SCACHE (tc_scache + ((threadIdx.x >> 5) * (TC_SCACHE_SLOTS * 32) + (threadIdx.x & 31)"
+            + (" * 2" if pair else "") + "))\n"
             "// divcall=1 moves the ~20-instruction IEEE division out of line (-18 % SASS); measured on B200 it\n"
             "// is 5-10 % slower than inline division (the call spills live operands), so inline is the default\n"
             "static __device__ __noinline__ double tc_div(double a, double b) { return a / b; }\n"
@@ -322,13 +461,15 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         size += len(src)
     files[f"part_{len(files):03d}.cu"] = "".join(cur)
     fp = fingerprint(pr)
-    if lockstep not in (1, 2, 4, 8):
-        raise ValueError("lockstep must be 1, 2, 4 or 8 warps per CTA")
+    if lockstep not in (1, 2, 3, 4, 6, 8, 12):
+        raise ValueError("lockstep must be 1, 2, 3, 4, 6, 8 or 12 warps per CTA (32*lockstep divides the batch stride)")
     if warps_per_sm % lockstep or not 1 <= warps_per_sm <= 32:
         raise ValueError("warps_per_sm must be a multiple of lockstep, at most 32")
     # `resident` > 0 caps the CTAs resident per SM below the register limit (a dynamic shared-memory
     # reservation nobody uses): fewer warps in flight = a larger share of the 126 MB L2 per warp
     smem = 0 if not resident else (227 * 1024 // resident) // 1024 * 1024 - 1024
+    if scache:
+        smem = scache * 8 * TILE * lockstep * (2 if pair else 1)
     if driver not in ("warp", "lanes", "queue") or (driver != "warp" and (tiles != 1 or lockstep != 1)):
         raise ValueError("driver must be 'warp', 'lanes' or 'queue' (lanes/queue: tiles=1, lockstep=1)")
     m = [head, ("#define TC_DRIVER_LANES 1\n" if driver != "warp" else ""),
@@ -369,6 +510,15 @@ __attribute__((visibility("default"))) int tcm_load(void) {{
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, tc_eval_kernel);
     if (e == cudaSuccess && TC_SMEM_BYTES)
         e = cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e == cudaSuccess && TC_SMEM_BYTES)
+        e = cudaFuncSetAttribute(tc_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    // the shared-memory cache must not cost residency: ask for the carve-out that holds TC_KMINBLOCKS CTAs
+    if (e == cudaSuccess && TC_SMEM_BYTES) {{
+        int pct = (int)((TC_KMINBLOCKS * (TC_SMEM_BYTES + 1024ll) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        e = cudaFuncSetAttribute(tc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }}
     return (int)e;
 }}
 // ipmPD_CSsolver() for every instance of the batch: ONE launch, the Newton loop stays on the device
@@ -381,6 +531,20 @@ __attribute__((visibility("default"))) int tcm_solve(const tc_device_image *P, d
         *P, mu0, maxIter, aeU, aeEq, status, iter, phase_first, phase_iters);
     return (int)cudaGetLastError();
 }}
+// CTAs of the solve kernel resident per SM as launched (the register budget allows TC_KMINBLOCKS)
+__attribute__((visibility("default"))) int tcm_occupancy(void) {{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tc_solve_kernel, TC_KBLOCK, TC_SMEM_BYTES) != cudaSuccess) return -1;
+    return n;
+}}
+// 1: scratchbook layout m[tile pair][slot][lane][2] (emitter option pair), 0: m[tile][slot][lane]
+__attribute__((visibility("default"))) int tcm_interleave(void) {{
+#ifdef TC_PAIR
+    return 1;
+#else
+    return 0;
+#endif
+}}
 // 1: the module's driver parks/resumes the solver loop between phase launches (warp driver, one warp per CTA)
 __attribute__((visibility("default"))) int tcm_phased(void) {{
 #if defined(TC_DRIVER_LANES)
@@ -391,7 +555,7 @@ __attribute__((visibility("default"))) int tcm_phased(void) {{
 }}
 // lazy evaluation of the parents of get function fn (classname_getOutputs)
 __attribute__((visibility("default"))) int tcm_eval(const tc_device_image *P, int fn, void *stream) {{
-    tc_eval_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, 0, (cudaStream_t)stream>>>(*P, fn);
+    tc_eval_kernel<<<(unsigned)(P->stride / (TC_KBLOCK * TC_TILES)), TC_KBLOCK, TC_SMEM_BYTES, (cudaStream_t)stream>>>(*P, fn);
     return (int)cudaGetLastError();
 }}
 }}

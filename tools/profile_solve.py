@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--divcall", type=int, default=-1, help="1: IEEE division out of line, 0: inline (-1: default)")
     ap.add_argument("--max-loads", type=int, default=0, help="scratchbook operands per chunk (0: default)")
     ap.add_argument("--warps-per-sm", type=int, default=0, help="resident warps per SM = register budget (0: default)")
+    ap.add_argument("--mopts", default="", help="further emitter options, k=v,k=v (integers)")
     args = ap.parse_args()
     from tenscalc_b200 import problems
     gen, sargs = problems.BUILDERS[args.workload]()
@@ -39,6 +40,9 @@ def main():
     opts = {k: v for k, v in dict(lockstep=args.lockstep, max_loads=args.max_loads,
                                       warps_per_sm=args.warps_per_sm, merge=args.merge, tiles=args.tiles,
                                       assume_global=args.assume_global, resident=args.resident).items() if v}
+    for kv in filter(None, args.mopts.split(",")):
+        k, v = kv.split("=")
+        opts[k] = int(v) if v.lstrip("-").isdigit() else v
     if args.driver:
         opts["driver"] = args.driver
     if args.prefetch >= 0:
