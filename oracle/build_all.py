@@ -14,7 +14,10 @@ CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}
 # ipmPDeq_CSsolver (equilibria): the reference's own driver is the only oracle (kind "ref")
 EQ_CONFIGS = [("matrix_game", {}), ("qsaddle", {}), ("qsaddle_latent", {}), ("qsaddle", {"useLDL": True}),
               ("matrix_game", {"skipAffine": False}),
-              ("qsaddle", {"addEye2Hessian": True, "adjustAddEye2Hessian": True})]   # regulariser control of the eq driver (:318-374)
+              ("qsaddle", {"addEye2Hessian": True, "adjustAddEye2Hessian": True}),   # regulariser control of the eq driver (:318-374)
+              # reduced Newton matrix of the equilibrium builder (ipmPDeqlat_CS.m:314-561): dlambda eliminated
+              ("qsaddle", {"smallerNewtonMatrix": True}), ("qsaddle_latent", {"smallerNewtonMatrix": True}),
+              ("matrix_game", {"smallerNewtonMatrix": True, "skipAffine": False})]
 
 
 # extra builds of the benchmark workload: the toolbox's default -O0 and -O2 beside the headline -O1

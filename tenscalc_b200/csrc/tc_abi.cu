@@ -284,7 +284,8 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     if (!s) return TC_EINVAL;
     s->device = device;
     s->batch = batch;
-    s->stride = (batch + 767) / 768 * 768;   // whole CTAs for every back end (TC_BLOCK = 256; 32*TC_LOCKSTEP divides 768)
+    s->stride = (batch + 1535) / 1536 * 1536;   // whole CTAs for every back end and launch shape: TC_BLOCK = 256,
+                                                // 32 * lockstep (1,2,3,4,6,8,12) * instances per lane (1,2,4 | pair) divides 1536
     const int64_t n_slots = ih[1], n_groups = ih[2], n_funcs = ih[3], n_sets = ih[4], n_out = ih[5],
                   tape_cells = ih[6], n_consts = ih[7], io_words = ih[8], n_persist = ih[11];
     s->n_slots = n_slots;

@@ -10,7 +10,7 @@ the "times lambda" symmetric KKT matrix
 
 its fixed-pattern LDL' factorisation, the Newton direction, step bounds and the
 multiplicative dual update.  Function names are the reference's ``*__`` names; the
-driver (device: ``csrc/ipm_driver.cuh``, oracle: the reference's own
+driver (device: ``csrc/tc_driver.cuh``, oracle: the reference's own
 ``lib/ipmPD_CSsolver.c``) calls exactly these.
 
 Host-side, offline.  Everything is expressed per scalar on the instruction table.

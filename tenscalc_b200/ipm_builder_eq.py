@@ -39,8 +39,6 @@ def build_ipm_eqlat(code: CSparse, u: List[int], d: List[int], x: List[int], f: 
                     addEye2Hessian: bool = False, skipAffine: bool = True, useLDL: bool = False,
                     smallerNewtonMatrix: bool = False, ordering=None) -> Dict[str, object]:
     tab: InstructionTable = code.tab
-    if smallerNewtonMatrix:
-        raise NotImplementedError("smallerNewtonMatrix=true (ipmPDeqlat_CS.m:310-561) is not built; the default is false")
     nU, nD, nX = len(u), len(d), len(x)
     nZ = nU + nD + nX
     nGu, nGd, nH = len(Gu), len(Gd), len(H)
@@ -134,25 +132,61 @@ def build_ipm_eqlat(code: CSparse, u: List[int], d: List[int], x: List[int], f: 
     ng = tab.add([(1, e) for e in norms if e is not None])
     code.declare_get("getNorminf_Grad__", [[zero if ng is None else ng]])                    # :238,247
 
-    # rows of WW in the reference's order; every row is the gradient of one residual with respect to w, except that
-    # the last block is diag(F./lambda) instead of the derivative with respect to lambda (:568-575,595-600)
-    n = nZ + nNu + nF
     residuals = Lf_u + Lg_d + Lf_x + Lg_x
     if any(r is None for r in residuals):
         raise ValueError("a stationarity condition is structurally zero: some optimisation variable does not enter its "
                          "player's Lagrangian")
-    WW: List[Dict[int, int]] = [grad_row(r) for r in residuals]
-    for e in G:
-        WW.append({k: v for k, v in grad_row(e).items() if k < nZ})                          # [G_z, 0, 0]
-    for k, e in enumerate(F):
-        row = {c: v for c, v in grad_row(e).items() if c < nZ}                               # [F_z, 0, diag(F./lambda)]
-        row[nZ + nNu + k] = tab.div(e, lam[k])
-        WW.append(row)
-    if len(WW) != n:
-        raise AssertionError("Newton matrix is not square")
     neg = tab.neg
-    b_a: List[Id] = [neg(r) for r in residuals] + [neg(e) for e in G] + [neg(e) for e in F]
     F_z = [{c: v for c, v in grad_row(e).items() if c < nZ} for e in F]
+    if smallerNewtonMatrix:
+        # ---- small matrix (:314-446): unknowns [z; nu]; dlambda = -lambda - LFF dz + mu./F is eliminated, ------
+        # LFF = diag(lambda./F) F_z (:304).  Row of a stationarity condition r: [r_z - r_lambda LFF, r_nu]; then [G_z, 0]
+        n = nZ + nNu
+        lamF = [tab.div(lam[k], F[k]) for k in range(nF)]
+        LFF = [{c: tab.mul([lamF[k], v]) for c, v in F_z[k].items()} for k in range(nF)]
+        r_l: List[Dict[int, int]] = []              # d residual / d lambda (Lf_ul, Lg_dl, Lf_xl, Lg_xl)
+        WW = []
+        for i, r in enumerate(residuals):
+            g_ = grad_row(r)
+            rl = {c - nZ - nNu: v for c, v in g_.items() if c >= nZ + nNu}
+            r_l.append(rl)
+            row: Dict[int, int] = {c: v for c, v in g_.items() if nZ <= c < nZ + nNu}
+            cols = sorted({c for c in g_ if c < nZ} | {c for k in rl for c in LFF[k]})
+            for c in cols:
+                corr = tab.dot((rl[k], LFF[k][c]) for k in sorted(rl) if c in LFF[k])
+                e = tab.add(([(1, g_[c])] if c in g_ else []) + ([(-1, corr)] if corr is not None else []))
+                if e is not None:
+                    row[c] = e
+            if nX == 0 and addEye2Hessian and i < nZ:                                        # :362-365 (no latent variables)
+                row[i] = tab.add([(1, row[i]), (1, e1)]) if i in row else e1
+            WW.append(row)
+        for j, e in enumerate(G):
+            row = {c: v for c, v in grad_row(e).items() if c < nZ}
+            if nX == 0 and addEye2Hessian:
+                row[nZ + j] = neg(e2)
+            WW.append(row)
+        if len(WW) != n:
+            raise AssertionError("Newton matrix is not square")
+        # right-hand sides (:338-361,383-403): the gradients of f + nu'G WITHOUT the inequality terms, which enter
+        # through the eliminated dlambda
+        ff = tab.add([(1, f)] + ([(1, tab.dot(zip(P1nu, Gu)))] if nGu else []) + ([(1, tab.dot(zip(P1xnu, H)))] if nX else []))
+        gg = tab.add([(1, g)] + ([(1, tab.dot(zip(P2nu, Gd)))] if nGd else []) + ([(1, tab.dot(zip(P2xnu, H)))] if nX else []))
+        grads = grad_wrt(ff, u) + grad_wrt(gg, d) + grad_wrt(ff, x) + grad_wrt(gg, x)
+        b_a = [neg(e) for e in grads] + [neg(e) for e in G]
+    else:
+        # ---- large matrix (:563-600): rows in the reference's order; every row is the gradient of one residual with
+        # respect to w, except that the last block is diag(F./lambda) instead of the derivative with respect to lambda
+        n = nZ + nNu + nF
+        WW = [grad_row(r) for r in residuals]
+        for e in G:
+            WW.append({k: v for k, v in grad_row(e).items() if k < nZ})                      # [G_z, 0, 0]
+        for k, e in enumerate(F):
+            row = {c: v for c, v in grad_row(e).items() if c < nZ}                           # [F_z, 0, diag(F./lambda)]
+            row[nZ + nNu + k] = tab.div(e, lam[k])
+            WW.append(row)
+        if len(WW) != n:
+            raise AssertionError("Newton matrix is not square")
+        b_a = [neg(r) for r in residuals] + [neg(e) for e in G] + [neg(e) for e in F]
 
     # ---- factorisation (:645-654) ---------------------------------------------------------------------------
     def symmetrise(M: List[Dict[int, int]], rhs: List[Id]):
@@ -188,35 +222,62 @@ def build_ipm_eqlat(code: CSparse, u: List[int], d: List[int], x: List[int], f: 
     def stepped(vars_: List[int], dv: List[Id], alpha: int) -> List[Id]:
         return [tab.add([(1, a), (1, tab.mul([alpha, b]))]) for a, b in zip(vars_, dv)]
 
+    def lam_step(dZ_: List[Id], with_mu: bool, meh: List[Id]) -> List[Id]:
+        """small matrix: dlambda = -lambda - LFF dz [+ mu./F] [- Mehrotra] (:466,516-524)"""
+        outl = []
+        for k in range(nF):
+            t = times_row(LFF[k], dZ_)
+            outl.append(tab.add([(-1, lam[k])] + ([(-1, t)] if t is not None else [])
+                                + ([(1, tab.div(mu, F[k]))] if with_mu else []) + ([(-1, meh[k])] if meh[k] is not None else [])))
+        return outl
+
+    def minus_rl(vec: List[Id], sign: int) -> List[Id]:
+        """sign * [Lf_ul; Lg_dl; Lf_xl; Lg_xl] vec, zero for the G rows (:358-361,484-494)"""
+        rows = [tab.dot((r_l[i][k], vec[k]) for k in sorted(r_l[i]) if vec[k] is not None) for i in range(len(residuals))]
+        return [None if e is None else (e if sign > 0 else neg(e)) for e in rows] + [None] * nG
+
+    def plus(a: List[Id], b: List[Id]) -> List[Id]:
+        return [tab.add(([(1, x)] if x is not None else []) + ([(1, y)] if y is not None else [])) for x, y in zip(a, b)]
+
     mehrotra: List[Id] = [None] * nF
-    if not skipAffine and nF > 0:                                                            # :656-713
+    if not skipAffine and nF > 0:                                                            # :656-713 / :433-497
         dx_a = fsolve(b_a)
-        dZ_a, dLam_a = dx_a[:nZ], dx_a[nZ + nNu:]
+        dZ_a = dx_a[:nZ]
+        dLam_a = lam_step(dZ_a, False, mehrotra) if smallerNewtonMatrix else dx_a[nZ + nNu:]
         newZ_a = stepped(z, dZ_a, aP)
         newLam_a = stepped(lam, dLam_a, aDi)
         newF_a = tab.substitute(F, dict(zip(z, newZ_a)))
         FzdZ_a = [times_row(F_z[k], dZ_a) for k in range(nF)]
         mAP = tab.clp(list(zip(F, FzdZ_a)))
         mAD = tab.clp(list(zip(lam, dLam_a)))
-        mehrotra = [tab.div(tab.mul([FzdZ_a[k], dLam_a[k]]), lam[k]) for k in range(nF)]
+        # Mehrotra correction: (F_z dz).*dlambda./lambda in the large system (:697), ./F in the small one (:481)
+        mehrotra = [tab.div(tab.mul([FzdZ_a[k], dLam_a[k]]), F[k] if smallerNewtonMatrix else lam[k]) for k in range(nF)]
         rho = tab.div(tab.dot(zip(newF_a, newLam_a)), gap)
         code.declare_get("getMaxAlphas_a__", [[big if mAP is None else mAP], [big if mAD is None else mAD]])
         code.declare_get("getMinF_a__", [[tab.minmax(newF_a, True)]])
         code.declare_get("getRho__", [[zero if rho is None else rho]])
 
-    # ---- combined direction (:716-768) -------------------------------------------------------------------------
-    b_s = [neg(r) for r in residuals] + [neg(e) for e in G]
-    b_s += [tab.add([(-1, F[k]), (-1, mehrotra[k]), (1, tab.div(mu, lam[k]))]) for k in range(nF)]
+    # ---- combined direction (:716-768 / :500-560) ---------------------------------------------------------------
+    if smallerNewtonMatrix:
+        b_s = list(b_a)
+        if nF > 0:
+            b_s = plus(b_s, minus_rl([tab.div(mu, F[k]) for k in range(nF)], -1))
+            if any(m is not None for m in mehrotra):
+                b_s = plus(b_s, minus_rl(mehrotra, +1))
+    else:
+        b_s = [neg(r) for r in residuals] + [neg(e) for e in G]
+        b_s += [tab.add([(-1, F[k]), (-1, mehrotra[k]), (1, tab.div(mu, lam[k]))]) for k in range(nF)]
     dx = fsolve(b_s)
     out["dx"] = dx
     if useLDL:                                   # WW and b_s were replaced by the symmetrised ones (:647-650)
         Ws, bs = symmetrise(WW, b_s)
     else:
         Ws, bs = WW, b_s
-    resid = [tab.add([(1, times_row(Ws[i], dx)), (-1, bs[i])]) for i in range(n)]
+    resid = [tab.add([(1, times_row(Ws[i], dx))] + ([(-1, bs[i])] if bs[i] is not None else [])) for i in range(n)]
     derr = tab.max_abs(resid)
     code.declare_get("getDirectionError__", [[zero if derr is None else derr]])              # :726
-    dZ, dNu, dLam = dx[:nZ], dx[nZ:nZ + nNu], dx[nZ + nNu:]
+    dZ, dNu = dx[:nZ], dx[nZ:nZ + nNu]
+    dLam = (lam_step(dZ, True, mehrotra) if nF else []) if smallerNewtonMatrix else dx[nZ + nNu:]
     newZ = stepped(z, dZ, aP)
     newNu = stepped(nu, dNu, aDe)
     newLam: List[Id] = []

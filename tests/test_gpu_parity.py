@@ -29,6 +29,9 @@ CASES = [("sls", 512, {}), ("mpc_dcmotor", 512, {}), ("l1l2", 128, {}), ("mpc_qu
          ("qsaddle", 256, {"useLDL": True}),                                  # normal equations + LDL' (ipmPDeqlat_CS.m:645-651)
          ("matrix_game", 256, {"skipAffine": False}),
          ("qsaddle", 256, {"addEye2Hessian": True, "adjustAddEye2Hessian": True}),     # regulariser retries (:318-374)
+         # reduced Newton matrix of the equilibrium builder (ipmPDeqlat_CS.m:314-561), also with latent variables and Mehrotra
+         ("qsaddle", 256, {"smallerNewtonMatrix": True}), ("qsaddle_latent", 256, {"smallerNewtonMatrix": True}),
+         ("matrix_game", 256, {"smallerNewtonMatrix": True, "skipAffine": False}),
          # min-max: cmex2minmaxCS -> ipmPDminmax_CSsolver (three regularisers, inertia control).  PARITY UNPINNED:
          # the oracle's driver is a C transcription of the reference's MATLAB solver (oracle/ipm_driver_minmax_port.c)
          ("minmax_box", 512, {}), ("minmax_box_latent", 512, {}), ("minmax_box", 256, {"N": 16})]                         # affine-scaling step of the eq driver (:326-398)
@@ -113,6 +116,41 @@ def test_tiles_option_is_bit_identical():
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     for a, b in zip(outs[0][2], outs[1][2]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("opts", [dict(pair=1, max_loads=14), dict(scache=24), dict(pair=1, max_loads=14, scache=12),
+                                  dict(lockstep=6, warps_per_sm=24), dict(prefetch=0)],
+                         ids=["pair", "scache", "pair+scache", "lockstep6", "noprefetch"])
+@pytest.mark.parametrize("name,batch", [("sls", 1000), ("mpc_dcmotor", 700)])
+def test_layout_options_are_bit_identical(name, batch, opts):
+    """emitter options that change where values live, not what is computed: `pair` (two instances per lane in
+    interleaved columns, 128-bit loads and stores; the set/gather/compaction kernels follow the layout through
+    tc_device_image::ilv), `scache` (per-lane software cache in shared memory, offline Belady plan), CTAs of 6
+    lockstep warps, no L2 prefetch -- same status, iterations and outputs as the default module, on a ragged batch,
+    and the same again after a set + re-solve on the same handle (stale lazy-evaluation state of the partner)"""
+    gen, args = generated(name)
+    P, V = problems.synthetic_inputs(name, gen, batch, seed=11)
+    P2, V2 = problems.synthetic_inputs(name, gen, batch, seed=12)
+    res = []
+    for o in ({}, opts):
+        obj = _solve(gen, args, P, V, batch, **o)
+        st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+        y = obj.getOutputs()
+        for n, _ in gen.parameters:                 # second solve on the same handle: half of the instances get
+            v = np.array(P[n], copy=True)           # new parameters, all get new initial values
+            v[..., ::2] = P2[n][..., ::2]
+            getattr(obj, "setP_" + n)(v)
+        for n, _ in gen.variables:
+            getattr(obj, "setV_" + n)(V2[n])
+        st2, it2, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+        res.append((st, it, y, st2, it2, obj.getOutputs()))
+        obj.close()
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    for x, y in zip(list(a[2]) + list(a[5]), list(b[2]) + list(b[5])):
+        assert np.array_equal(x, y)
+    assert (a[0] == 0).mean() > 0.5
 
 
 @pytest.mark.parametrize("driver", ["lanes", "queue"])

@@ -99,6 +99,30 @@ def test_equilibrium_solutions_are_saddle_points():
     assert (Ad.min(0) > v - 1e-3).all() and (uA.max(0) < v + 1e-3).all()
 
 
+@pytest.mark.parametrize("name,kw", [("qsaddle", {}), ("qsaddle_latent", {}), ("matrix_game", {"skipAffine": False})])
+def test_equilibrium_reduced_newton_matrix_matches_large(name, kw):
+    """smallerNewtonMatrix=true of the equilibrium builder (ipmPDeqlat_CS.m:314-561: dlambda eliminated, unknowns
+    [z; nu]) under the reference's unmodified driver: the Newton steps are the large system's in exact arithmetic, so
+    every instance converges, iteration counts agree within one, and the equilibria agree to the solver's accuracy
+    (a step-length tie that rounding breaks differently moves single instances by more than rounding)"""
+    from oracle.oracle import Oracle
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("/root/reference not mounted: the reference-driver libraries of these variants are built on demand")
+    res = []
+    for small in (False, True):
+        gen, args = generated(name, **kw, smallerNewtonMatrix=small)
+        P, V = problems.synthetic_inputs(name, gen, 48, seed=3)
+        o = Oracle(gen, "ref")
+        o.build()
+        res.append(o.solve_batch(P, V, args["mu0"], args["maxIter"])[:3])
+    (st_l, it_l, out_l), (st_s, it_s, out_s) = res
+    assert (st_l == 0).all() and (st_s == 0).all()
+    assert np.abs(it_l.astype(int) - it_s.astype(int)).max() <= 1
+    for k in out_l:
+        assert np.abs(out_l[k] - out_s[k]).max() < 2e-3
+        assert np.median(np.abs(out_l[k] - out_s[k]).reshape(-1, out_l[k].shape[-1]).max(0)) < 1e-6
+
+
 def test_minmax_port_solves_the_box_game():
     """ipmPDminmax_CSsolver (PARITY UNPINNED, oracle/ipm_driver_minmax_port.c) on cases 5 / 5.5 of
     examples/minmaxTest.m: min_u max_d |u+d+a|^2-2|d+2|^2 on -2<=u<=2, -1<=d<=1 has d=-1, u=clip(1-a,-2,2)"""
