@@ -67,37 +67,47 @@ __device__ __forceinline__ void tcd_cp_async8(double *smem_dst, const double *gm
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
 }
 
-template <int NT>   // NT = n/8 tile columns
-__global__ void __launch_bounds__(TCD_THREADS) tcd_gram_kernel(const double *__restrict__ A, const double *__restrict__ b,
-                                                              int64_t N, double *__restrict__ H0,
-                                                              double *__restrict__ g0, double *__restrict__ c0) {
+// body of the Gram kernel for the block row that starts at tile column TC0 (= 8 * blockIdx.y): with TC0 a
+// compile-time constant every fragment address is an immediate offset from two per-lane base pointers and the
+// tile loop carries no predicate -- two instructions (LDS.64 + DMMA) per tile instead of eleven
+template <int NT, int TC0>
+__device__ __forceinline__ void tcd_gram_body(const double *__restrict__ A, const double *__restrict__ b, int64_t N,
+                                              double *__restrict__ H0, double *__restrict__ g0, double *__restrict__ c0,
+                                              double *sm) {
     constexpr int n = NT * 8;
     constexpr int STAGE = (n + 8) * TCD_GLDS;       // doubles per shared-memory stage
-    extern __shared__ double sm[];                 // [2][(n + 8)][TCD_GLDS]
+    constexpr int j0 = TC0 * 8;                     // only the columns >= j0 are needed by this block
     const int64_t inst = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tr = blockIdx.y * 8 + warp;          // tile row of this warp
-    const int tc0 = blockIdx.y * 8;                // first tile column of the block (upper triangle by blocks)
-    const int j0 = tc0 * 8;                        // only the columns >= j0 are needed by this block
+    const int tr = TC0 + warp;                      // tile row of this warp
     const double *Ai = A + (size_t)inst * (size_t)N * n;
     const double *bi = b + (size_t)inst * (size_t)N;
-    double acc[NT + 1][2];
+    double acc[NT + 1 - TC0][2];
 #pragma unroll
-    for (int t = 0; t <= NT; t++) acc[t][0] = acc[t][1] = 0.0;
+    for (int t = 0; t <= NT - TC0; t++) acc[t][0] = acc[t][1] = 0.0;
     double bsq = 0.0;
     const bool active = tr < NT;
     for (int e = threadIdx.x; e < 2 * 7 * TCD_GLDS; e += TCD_THREADS)          // zero padding of the b tile, both stages
         sm[(e / (7 * TCD_GLDS)) * STAGE + (n + 1) * TCD_GLDS + e % (7 * TCD_GLDS)] = 0.0;
     // cp.async double buffering: stage s+1 (rows k0+32.. of the needed columns, 256 contiguous bytes per warp and
-    // column, written transposed [column][k]) is in flight while the tensor cores work on stage s
+    // column, written transposed [column][k]) is in flight while the tensor cores work on stage s.  Warp w fetches
+    // the columns j0+w, j0+w+8, ..; warp 0 also fetches b (column n of the stage).
+    const double *src0 = Ai + lane + (size_t)N * (j0 + warp);
+    double *dst0 = sm + (j0 + warp) * TCD_GLDS + lane;
     auto issue = [&](int64_t k0, int buf) {
-        const int64_t k = k0 + lane;
-        for (int j = j0 + warp; j <= n; j += TCD_THREADS / 32)
-            tcd_cp_async8(sm + buf * STAGE + j * TCD_GLDS + lane, j < n ? Ai + k + (size_t)N * j : bi + k, k < N);
+        const bool ok = k0 + lane < N;
+        const double *src = src0 + k0;
+        double *dst = dst0 + buf * STAGE;
+#pragma unroll 4
+        for (int j = j0 + warp; j < n; j += TCD_THREADS / 32, src += (size_t)N * (TCD_THREADS / 32), dst += (TCD_THREADS / 32) * TCD_GLDS)
+            tcd_cp_async8(dst, src, ok);
+        if (warp == 0) tcd_cp_async8(sm + buf * STAGE + n * TCD_GLDS + lane, bi + k0 + lane, ok);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     issue(0, 0);
     int buf = 0;
+    const int fa = (tr * 8 + (lane >> 2)) * TCD_GLDS + (lane & 3);     // A fragment: rows of this warp's tile row
+    const int fb = (j0 + (lane >> 2)) * TCD_GLDS + (lane & 3);        // B fragment of tile column TC0; +8*TCD_GLDS per tile
     for (int64_t k0 = 0; k0 < N; k0 += TCD_KC, buf ^= 1) {
         if (k0 + TCD_KC < N) {
             issue(k0 + TCD_KC, buf ^ 1);
@@ -107,18 +117,15 @@ __global__ void __launch_bounds__(TCD_THREADS) tcd_gram_kernel(const double *__r
         }
         __syncthreads();                           // stage `buf` is complete and visible
         const double *st = sm + buf * STAGE;
-        if (blockIdx.y == 0 && warp == 0) { const double v = st[n * TCD_GLDS + lane]; bsq += v * v; }
+        if (TC0 == 0 && warp == 0) { const double v = st[n * TCD_GLDS + lane]; bsq += v * v; }
         if (active) {
+            const double *pa = st + fa, *pb = st + fb;
 #pragma unroll
             for (int kk = 0; kk < TCD_KC / 4; kk++) {
-                const double a = st[(tr * 8 + (lane >> 2)) * TCD_GLDS + 4 * kk + (lane & 3)];
+                const double a = pa[4 * kk];
 #pragma unroll
-                for (int t = 0; t <= NT; t++) {
-                    if (t >= tc0) {            // uniform per CTA
-                        const double bf = st[(t * 8 + (lane >> 2)) * TCD_GLDS + 4 * kk + (lane & 3)];
-                        tcd_dmma(acc[t][0], acc[t][1], a, bf);
-                    }
-                }
+                for (int t = 0; t <= NT - TC0; t++)
+                    tcd_dmma(acc[t][0], acc[t][1], a, pb[t * 8 * TCD_GLDS + 4 * kk]);
             }
         }
         __syncthreads();                           // everybody is done with `buf` before the next issue overwrites it
@@ -128,24 +135,36 @@ __global__ void __launch_bounds__(TCD_THREADS) tcd_gram_kernel(const double *__r
         const int i = tr * 8 + (lane >> 2);
         double *Hi = H0 + (size_t)inst * n * n;
 #pragma unroll
-        for (int t = 0; t < NT; t++) {
-            if (t >= tc0) {
+        for (int t = 0; t < NT - TC0; t++) {
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int j = t * 8 + 2 * (lane & 3) + q;
-                    if (j >= i) {                  // the upper entry is authoritative: exactly symmetric H0
-                        const double v = scale * acc[t][q];
-                        Hi[i + (size_t)n * j] = v;
-                        Hi[j + (size_t)n * i] = v;
-                    }
+            for (int q = 0; q < 2; q++) {
+                const int j = (TC0 + t) * 8 + 2 * (lane & 3) + q;
+                if (j >= i) {                      // the upper entry is authoritative: exactly symmetric H0
+                    const double v = scale * acc[t][q];
+                    Hi[i + (size_t)n * j] = v;
+                    Hi[j + (size_t)n * i] = v;
                 }
             }
         }
-        if ((lane & 3) == 0) g0[(size_t)inst * n + i] = scale * acc[NT][0];
+        if ((lane & 3) == 0) g0[(size_t)inst * n + i] = scale * acc[NT - TC0][0];
     }
-    if (blockIdx.y == 0 && warp == 0) {
+    if (TC0 == 0 && warp == 0) {
         for (int o = 16; o; o >>= 1) bsq += __shfl_xor_sync(0xffffffffu, bsq, o);
         if (lane == 0) c0[inst] = bsq / (double)N;
+    }
+}
+
+template <int NT>   // NT = n/8 tile columns
+__global__ void __launch_bounds__(TCD_THREADS) tcd_gram_kernel(const double *__restrict__ A, const double *__restrict__ b,
+                                                              int64_t N, double *__restrict__ H0,
+                                                              double *__restrict__ g0, double *__restrict__ c0) {
+    extern __shared__ double sm[];                 // [2][(n + 8)][TCD_GLDS]
+    // upper triangle by 64-row blocks: block row y needs the tile columns >= 8 y (uniform per CTA)
+    if (blockIdx.y == 0) tcd_gram_body<NT, 0>(A, b, N, H0, g0, c0, sm);
+    if constexpr (NT > 8) { if (blockIdx.y == 1) tcd_gram_body<NT, 8>(A, b, N, H0, g0, c0, sm); }
+    if constexpr (NT > 16) {
+        if (blockIdx.y == 2) tcd_gram_body<NT, 16>(A, b, N, H0, g0, c0, sm);
+        if (blockIdx.y == 3) tcd_gram_body<NT, 24>(A, b, N, H0, g0, c0, sm);
     }
 }
 
