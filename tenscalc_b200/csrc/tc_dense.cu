@@ -244,39 +244,44 @@ __device__ __forceinline__ void tcd_trailing(double *__restrict__ W22, int n, in
                                              const tcd_smem &S, unsigned long long &flops) {
     const int lane = threadIdx.x & 31;
     const int rows = mt - tj0;                                    // tile rows tj0 .. mt-1 have tiles in the range
+    // per-lane bases: the C fragment of tile (ti, tj) is W22[8 ti + lane/4 + n (8 tj + 2 (lane%4) + {0,1})], the B
+    // fragment of tile column tj and step kk is Ls[(8 tj + lane/4) * TCD_LDS + 4 kk + lane%4] (indices fit an int)
+    const int cb = (lane >> 2) + n * (2 * (lane & 3));
+    const double *lb = S.Ls + (lane >> 2) * TCD_LDS + (lane & 3);
+    const int n8 = 8 * n;
+    unsigned long long done = 0;
     for (int q = wid; q < rows; q += nw) {
         const int ti = tj0 + ((q & 1) ? (q >> 1) : (rows - 1 - (q >> 1)));
         const int tend = min(ti + 1, tj1);
         double af[TCD_NB / 4];
 #pragma unroll
-        for (int kk = 0; kk < TCD_NB / 4; kk++)
-            af[kk] = S.Ls[(ti * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)] * S.dW[4 * kk + (lane & 3)];
-        const int r = ti * 8 + (lane >> 2);
-        for (int t0 = tj0; t0 < tend; t0 += 4) {
-            double c0[4], c1[4];
+        for (int kk = 0; kk < TCD_NB / 4; kk++) af[kk] = lb[ti * 8 * TCD_LDS + 4 * kk] * S.dW[4 * kk + (lane & 3)];
+        double *pc = W22 + cb + 8 * ti + tj0 * n8;                // tile (ti, tj0); + n8 per tile column
+        const double *pl = lb + tj0 * 8 * TCD_LDS;
+        int t0 = tj0;
+        for (; t0 + 4 <= tend; t0 += 4, pc += 4 * n8, pl += 4 * 8 * TCD_LDS) {     // four tiles: eight loads in flight
+            double c[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { c[u][0] = pc[u * n8]; c[u][1] = pc[u * n8 + n]; }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (t0 + u < tend) {
-                    const int c = (t0 + u) * 8 + 2 * (lane & 3);
-                    c0[u] = W22[r + (size_t)n * c];
-                    c1[u] = W22[r + (size_t)n * (c + 1)];
-                }
-            }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (t0 + u < tend) {
-                    const int tj = t0 + u;
-#pragma unroll
-                    for (int kk = 0; kk < TCD_NB / 4; kk++)
-                        tcd_dmma(c0[u], c1[u], af[kk], S.Ls[(tj * 8 + (lane >> 2)) * TCD_LDS + 4 * kk + (lane & 3)]);
-                    const int c = tj * 8 + 2 * (lane & 3);
-                    W22[r + (size_t)n * c] = c0[u];
-                    W22[r + (size_t)n * (c + 1)] = c1[u];
-                    if (lane == 0) flops += 2ull * 8 * 8 * TCD_NB;
-                }
+                for (int kk = 0; kk < TCD_NB / 4; kk++) tcd_dmma(c[u][0], c[u][1], af[kk], pl[u * 8 * TCD_LDS + 4 * kk]);
+                pc[u * n8] = c[u][0];
+                pc[u * n8 + n] = c[u][1];
             }
+            done += 4;
+        }
+        for (; t0 < tend; t0++, pc += n8, pl += 8 * TCD_LDS) {                    // the row's last one to three tiles
+            double c0 = pc[0], c1 = pc[n];
+#pragma unroll
+            for (int kk = 0; kk < TCD_NB / 4; kk++) tcd_dmma(c0, c1, af[kk], pl[4 * kk]);
+            pc[0] = c0;
+            pc[n] = c1;
+            done += 1;
         }
     }
+    if (lane == 0) flops += done * (2ull * 8 * 8 * TCD_NB);
 }
 
 // Blocked right-looking LDL' of the symmetric matrix whose LOWER triangle is in W (n x n, column-major), in place:
