@@ -70,6 +70,8 @@ def parse_args():
                     help="benchmarked instances re-solved by the CPU oracle after the timed region (0: skip)")
     ap.add_argument("--no-strong", action="store_true",
                     help="N>1: skip the strong-scaling leg (the BASELINE batch split over the N GPUs)")
+    ap.add_argument("--phases", default="", help="iteration budget of the phases of a phased solve, e.g. 1x40,2x12,4x16,8x16,16x16,32 "
+                                                  "(last repeats; default: the library's schedule)")
     ap.add_argument("--ordering", default="", help="elimination ordering of the generator (default: symamd)")
     ap.add_argument("--backend", default="compiled", choices=["compiled", "tape"],
                     help="compiled: per-problem sm_100a module (default); tape: generic interpreter")
@@ -345,9 +347,23 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
     # batch) run next to the bulk of the following batches instead of holding the GPU alone
     depth = max(1, min(args.pipeline, K))
     mopts = _mopts(args)
-    objs = [gen(B, device=local_rank, backend=args.backend, **mopts) for _ in range(depth)]
+    # as many handles as asked for and as fit: a handle costs its scratchbook (18 GB for mpc_quadcopter at 65 536
+    # instances) plus the parking pool of the phased solve; 10 % of the device stays free for the I/O arrays
+    free0, total_mem = torch.cuda.mem_get_info()
+    objs = [gen(B, device=local_rank, backend=args.backend, **mopts)]
+    objs[0].synchronize()
+    per_handle = max(free0 - torch.cuda.mem_get_info()[0], objs[0].scratch_bytes()) * 1.08
+    depth = max(1, min(depth, 1 + int((torch.cuda.mem_get_info()[0] - 0.10 * total_mem) // per_handle)))
+    objs += [gen(B, device=local_rank, backend=args.backend, **mopts) for _ in range(depth - 1)]
     obj = objs[0]
     assert obj.has_module() == (args.backend == "compiled")
+    if args.phases:
+        ph = []
+        for tok in args.phases.split(","):
+            a, _, b = tok.partition("x")
+            ph += [int(a)] * (int(b) if b else 1)
+        for o in objs:
+            o.set_phased(True, ph)
     exts = [torch.cuda.ExternalStream(o.stream_ptr(), device=torch.device("cuda", local_rank)) for o in objs]
     mu0, maxIter = sargs["mu0"], sargs["maxIter"]
     d_outs = [[torch.empty((B, n), dtype=torch.float64, device="cuda") for n in out_sizes] for _ in objs]

@@ -44,6 +44,80 @@ def test_literals_are_exact():
         assert float.fromhex(emit_cuda._lit(v)) == v if "x" in emit_cuda._lit(v) else float(emit_cuda._lit(v)) == v
 
 
+@pytest.mark.parametrize("capacity", [4, 24, 75])
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor"])
+def test_scache_plan_is_consistent(name, capacity):
+    """the offline shared-memory cache plan (emit_cuda.plan_scache): replay it chunk by chunk -- every value a
+    chunk takes from the cache is in the slot the plan names, nothing is read from the scratchbook that was never
+    stored there, at most `capacity` slots are live, and a bigger cache never loads more"""
+    gen, _ = generated(name)
+    pr = gen.problem
+    tab = pr.tab
+    ext = emit_cuda.external_values(pr)
+    const = (it.I_load, it.I_2)
+    total = 0
+    for g, members in enumerate(pr.groups):
+        chunks = emit_cuda.chunk_group(pr, members, 1536, 28)
+        reads, makes = [], []
+        for ch in chunks:
+            have, rs, ms = set(), [], []
+            for i in ch:
+                if tab.types[i] in (it.I_set,) + const:
+                    continue
+                for q in tab.operands[i]:
+                    if tab.types[q] not in const and q not in have:
+                        have.add(q)
+                        rs.append(q)
+                have.add(i)
+                ms.append(i)
+            reads.append(rs)
+            makes.append(ms)
+        plan, to_hbm = emit_cuda.plan_scache(reads, makes, ext, capacity)
+        made_all = {i for ms in makes for i in ms}
+        assert made_all & ext <= to_hbm                       # everything somebody outside the group reads is stored
+        slots = {}                                            # slot -> value, as the emitted code leaves it
+        in_hbm = set()                                        # values of this group that reached the scratchbook
+        for (from_smem, to_smem), rs, ms in zip(plan, reads, makes):
+            for q, sl in from_smem.items():
+                assert slots.get(sl) == q, (g, q, sl)
+            for q in rs:
+                if q not in from_smem:
+                    total += 1
+                    assert q not in made_all or q in in_hbm, (g, q)     # produced earlier in the group: must have been stored
+            for q, sl in to_smem:
+                assert 0 <= sl < capacity and (q in rs or q in ms)
+                slots[sl] = q
+            in_hbm |= {i for i in ms if i in to_hbm}
+            assert len(set(slots)) <= capacity
+    loads = {}
+    for c in (0, capacity):
+        st = emit_cuda.emit_module(gen, lockstep=8, warps_per_sm=24, max_loads=28, scache=c)[1]["total"]
+        loads[c] = st["loads"] + st["stores"]
+    assert loads[capacity] <= loads[0]
+    assert total > 0
+
+
+def test_pair_layout_emission():
+    """`pair`: two instances per lane in interleaved columns -- every scratchbook access of a group is a 16-byte
+    vector at twice the slot stride, the arithmetic is emitted once per instance, copies stay per instance"""
+    gen, _ = generated("sls")
+    files, st = emit_cuda.emit_module(gen, lockstep=8, warps_per_sm=24, max_loads=14, pair=1)
+    ref = emit_cuda.emit_module(gen, lockstep=8, warps_per_sm=24, max_loads=14)[1]
+    assert st["total"]["loads"] == ref["total"]["loads"] and st["total"]["stores"] == ref["total"]["stores"]
+    main = files["main.cu"]
+    assert "#define TC_PAIR 1" in main and "#define TC_TILES 2" in main and "tcm_interleave" in main
+    body = "".join(v for k, v in files.items() if k.startswith("part_"))
+    groups = [ln for ln in body.splitlines() if ln.startswith("const double2 v")]
+    assert groups and all(re.fullmatch(r"const double2 v\d+=\*\(const double2 \*\)\(mt\+(\d+)\);", ln) for ln in groups)
+    assert all(int(re.search(r"mt\+(\d+)", ln).group(1)) % 64 == 0 for ln in groups)          # slot stride 2 x 32 doubles
+    xs = len(re.findall(r"const double v\d+x=", body))
+    ys = len(re.findall(r"const double v\d+y=", body))
+    assert xs == ys > 0
+    assert "make_double2(" in body
+    with pytest.raises(ValueError):
+        emit_cuda.emit_module(gen, pair=1, driver="lanes")
+
+
 @pytest.mark.parametrize("name", ["sls", "mpc_dcmotor"])
 def test_chunks_cover_every_instruction_once(name):
     gen, _ = generated(name)
