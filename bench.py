@@ -369,9 +369,21 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
     d_outs = [[torch.empty((B, n), dtype=torch.float64, device="cuda") for n in out_sizes] for _ in objs]
     d_stats = [(torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda"))
                for _ in objs]
-    h_outs = [[torch.empty((B, n), dtype=torch.float64).pin_memory() for n in out_sizes] for _ in objs]
+    # end-to-end arm: `nbuf` sets of pinned host result buffers per handle, so that the next batch of a handle is
+    # queued (host -> device copy, solve, device -> host copy, all stream-ordered) while its previous one is still
+    # running -- the host waits for a step only when it needs that step's buffers again.  Two sets when the host
+    # has the memory for them (1.3 GB per set for mpc_quadcopter), else one (the host then blocks per step).
+    set_bytes = 8 * B * sum(out_sizes) + 8 * B
+    try:
+        avail = next(int(ln.split()[1]) * 1024 for ln in open("/proc/meminfo") if ln.startswith("MemAvailable"))
+    except (OSError, StopIteration):
+        avail = 0
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    nbuf = 2 if with_e2e and 2 * depth * set_bytes * local_world < 0.4 * avail else 1
+    nsets = depth * nbuf if with_e2e else 1
+    h_outs = [[torch.empty((B, n), dtype=torch.float64).pin_memory() for n in out_sizes] for _ in range(nsets)]
     h_stats = [(torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
-               for _ in objs]
+               for _ in range(nsets)]
 
     def step_device(i):
         o = objs[i % depth]
@@ -380,14 +392,19 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
         o.solve_device_ptr(d_stats[i % depth][0].data_ptr(), d_stats[i % depth][1].data_ptr(), mu0, maxIter)
         o.get_outputs_ptrs([t.data_ptr() for t in d_outs[i % depth]], device=True)
 
-    def e2e_submit(i):
+    e2e_done = {}
+
+    def e2e_submit(i):         # everything of step i is enqueued on its handle's stream; nothing blocks
         o = objs[i % depth]
         for k, t in h_in.items():
             o.set_packed(k, t.numpy())
-        o.solve_async(h_stats[i % depth][0].numpy(), h_stats[i % depth][1].numpy(), mu0, maxIter)
+        o.solve_async(h_stats[i % nsets][0].numpy(), h_stats[i % nsets][1].numpy(), mu0, maxIter)
+        o.get_outputs_ptrs([t.data_ptr() for t in h_outs[i % nsets]], device=False, sync=False)
+        e2e_done[i] = torch.cuda.Event()
+        e2e_done[i].record(exts[i % depth])
 
     def e2e_collect(i):        # blocks until step i is complete and its results are in host memory
-        objs[i % depth].get_outputs_ptrs([t.data_ptr() for t in h_outs[i % depth]], device=False)
+        e2e_done.pop(i).synchronize()
 
     def all_sync():
         for o in objs:
@@ -441,19 +458,21 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            if i >= depth:
-                e2e_collect(i - depth)
+            if i >= nsets:         # the host needs the buffers of step i - nsets again: that step must be complete
+                e2e_collect(i - nsets)
             e2e_submit(i)
-        for i in range(max(0, K - depth), K):
+        for i in range(max(0, K - nsets), K):
             e2e_collect(i)
         all_sync()
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0)     # host clock: the region starts and ends on the host
-        conv_e2e = int((h_stats[last][0].numpy() == 0).sum())
+        hl = (K - 1) % nsets
+        conv_e2e = int((h_stats[hl][0].numpy() == 0).sum())
         if parity is not None:     # the host-buffer path must give the device-pointer path's results
             parity["e2e_equals_device_arm"] = bool(
-                np.array_equal(h_stats[last][0].numpy(), st) and np.array_equal(h_stats[last][1].numpy(), it))
-    res = dict(B=B, depth=depth, total_ms=total_ms, e2e_ms=e2e_ms, solve_ms=solve_ms, launches=launches,
+                np.array_equal(h_stats[hl][0].numpy(), st) and np.array_equal(h_stats[hl][1].numpy(), it)
+                and all(np.array_equal(a.numpy(), b.cpu().numpy()) for a, b in zip(h_outs[hl], d_outs[last])))
+    res = dict(B=B, depth=depth, nbuf=nbuf, total_ms=total_ms, e2e_ms=e2e_ms, solve_ms=solve_ms, launches=launches,
                counts=counts, st=st, it=it, conv_e2e=conv_e2e, clk=clk, parity=parity,
                scratch_bytes=obj.scratch_bytes())
     for o in objs:
@@ -613,7 +632,10 @@ def run_ours(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {
                 "value": conv_e2e_all * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-                "h2d_bytes_per_step": int(io["h2d"] * B), "d2h_bytes_per_step": int(io["d2h"] * B)},
+                "h2d_bytes_per_step": int(io["h2d"] * B), "d2h_bytes_per_step": int(io["d2h"] * B),
+                "api": "tc_set (pinned host arrays) -> tc_solve_async -> tc_get_outputs_async into pinned host arrays; "
+                       f"{r['nbuf']} set(s) of host result buffers per handle: the host waits for a step when it needs "
+                       "that step's buffers again"},
             "gpu_launches": int(launches_all),
             "clocks": r["clk"],
         }

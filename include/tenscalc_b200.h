@@ -100,6 +100,11 @@ int tc_set_phases(tc_solver *s, const int32_t *iterations_per_phase, int n);
 /* <class>_getOutputs: y[k] is double[batch][tc_output_size(k)], caller-allocated. */
 int tc_get_outputs(tc_solver *s, double *const *y);
 int tc_get_outputs_device(tc_solver *s, double *const *d_y);
+/* tc_get_outputs without the final host synchronisation: the gather kernels and the copies into the
+ * (pinned) host arrays are only enqueued; the arrays are complete after tc_synchronize, or after an event
+ * the caller records on tc_stream(s).  With tc_set + tc_solve_async + tc_get_outputs_async a caller can
+ * queue the next batch on a handle before the previous one has finished (two sets of host buffers). */
+int tc_get_outputs_async(tc_solver *s, double *const *y);
 
 /* Device-resident warm start of a receding-horizon loop.  The reference's MPC examples feed outputs of
  * one solve back as the initial primal values of the next -- `out=getOutputs(obj); ...

@@ -692,7 +692,7 @@ int tc_get_outputs_device(tc_solver *s, double *const *d_y) {
     return (int)cudaGetLastError();
 }
 
-int tc_get_outputs(tc_solver *s, double *const *y) {
+int tc_get_outputs_async(tc_solver *s, double *const *y) {
     if (!s || !y) return TC_EINVAL;
     TC_CUDA(cudaSetDevice(s->device));
     TC_CUDA((cudaError_t)tc_launch_eval(s, (int)FN_getOutputs));
@@ -705,6 +705,12 @@ int tc_get_outputs(tc_solver *s, double *const *y) {
         TC_CUDA(cudaMemcpyAsync(y[k], s->d_stage, (size_t)n * s->batch * sizeof(double), cudaMemcpyDeviceToHost,
                                 s->stream));
     }
+    return (int)cudaGetLastError();
+}
+
+int tc_get_outputs(tc_solver *s, double *const *y) {
+    int rc = tc_get_outputs_async(s, y);
+    if (rc) return rc;
     TC_CUDA(cudaStreamSynchronize(s->stream));
     return (int)cudaGetLastError();
 }

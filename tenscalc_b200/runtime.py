@@ -47,6 +47,7 @@ ABI = [
     ("tc_set_phases", ctypes.c_int, [ctypes.c_void_p, _ip, ctypes.c_int]),
     ("tc_get_outputs", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     ("tc_get_outputs_device", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    ("tc_get_outputs_async", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     ("tc_feedback", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _ip, _ip]),
     ("tc_synchronize", ctypes.c_int, [ctypes.c_void_p]),
     ("tc_stream", ctypes.c_void_p, [ctypes.c_void_p]),
@@ -277,10 +278,12 @@ class BatchedSolver:
         _check(self._lib.tc_solve_async(self._h, ctypes.byref(mu), ctypes.byref(mi), ctypes.byref(si), ae,
                                         status.ctypes.data_as(ctypes.c_void_p), it.ctypes.data_as(ctypes.c_void_p)))
 
-    def get_outputs_ptrs(self, ptrs: Sequence[int], device: bool) -> None:
-        """getOutputs into caller-owned buffers, one double[batch][n_k] per output"""
+    def get_outputs_ptrs(self, ptrs: Sequence[int], device: bool, sync: bool = True) -> None:
+        """getOutputs into caller-owned buffers, one double[batch][n_k] per output; ``sync=False`` with host
+        buffers only enqueues the gathers and the copies (``tc_get_outputs_async``: pinned buffers, complete
+        after ``synchronize()`` or an event recorded on the handle's stream)"""
         arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
-        fn = self._lib.tc_get_outputs_device if device else self._lib.tc_get_outputs
+        fn = self._lib.tc_get_outputs_device if device else (self._lib.tc_get_outputs if sync else self._lib.tc_get_outputs_async)
         _check(fn(self._h, arr))
 
     def feedback(self, pairs: Dict[str, str]) -> None:
