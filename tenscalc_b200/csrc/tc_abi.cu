@@ -496,7 +496,8 @@ int tc_attach_module(tc_solver *s, const char *path, const char *fingerprint) {
         }
     }
     s->module = h;
-    s->img.ilv = ilv ? ilv() : 0;   // scratchbook layout of the module; nothing has been written yet (tc_create + attach)
+    s->img.ilv = ilv ? (ilv() == 1) : 0;   // scratchbook layout of the module (1: pair, 2: wide tiles); nothing has
+    s->img.wide = ilv ? (ilv() == 2) : 0;  // been written yet (tc_create + attach)
     s->mod_solve = solve;
     s->mod_eval = eval;
     s->mod_phased = phs ? phs() : 0;

@@ -114,12 +114,15 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     // 1: m[tile pair][slot][lane][2] -- the two instances of a lane sit side by side, so one 128-bit access
     // moves slot s of both (set by tc_attach_module from the module, before anything is written)
     int32_t ilv;
-    int32_t pad2_;
+    // 1: tiles of 64 instances, m[tile][slot][64] (emitter option wide): the two warps of a lockstep CTA that sit on
+    // neighbouring 32-instance blocks touch the two 256-byte halves of one 512-byte segment at about the same time
+    int32_t wide;
 };
 #define TC_PS_ND 12
 #define TC_PS_NI 2
 
 // address of scratchbook slot `slot` of instance `inst`
-#define TC_M(P, slot, inst)                                                                                   \
-    ((P).m[(((size_t)((inst) >> (5 + (P).ilv)) * (size_t)(P).n_slots + (size_t)(slot)) * TC_TILE << (P).ilv) + \
-           ((size_t)((inst) & 31) << (P).ilv) + (((inst) >> 5) & ((1 << (P).ilv) - 1))])
+#define TC_M(P, slot, inst)                                                                                        \
+    ((P).m[(((size_t)((inst) >> (5 + (P).ilv + (P).wide)) * (size_t)(P).n_slots + (size_t)(slot)) * TC_TILE            \
+            << ((P).ilv + (P).wide)) +                                                                                 \
+           ((P).ilv ? ((size_t)((inst) & 31) << 1) + (((inst) >> 5) & 1) : (size_t)((inst) & ((32 << (P).wide) - 1)))])

@@ -44,7 +44,7 @@
 #endif
 // doubles between two slots of one instance: 32, or 64 when the two instances of a lane are interleaved
 // (emitter option pair, tc_device_image::ilv = 1)
-#ifdef TC_PAIR
+#if defined(TC_PAIR) || defined(TC_WIDE)
 #define TC_SLOT_STRIDE (2 * TC_TILE)
 #else
 #define TC_SLOT_STRIDE TC_TILE

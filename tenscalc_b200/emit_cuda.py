@@ -203,7 +203,7 @@ def plan_scache(reads: List[List[int]], makes: List[List[int]], ext: Set[int], c
 def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                max_loads: int = 96, prefetch: int = 1, merge: int = 1,
                assume_global: int = 0, barrier: int = 0, scache: int = 0,
-               pair: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+               pair: int = 0, wide: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
     """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics.
 
     ``pair``: every lane carries TWO instances whose scratchbook columns are interleaved
@@ -213,7 +213,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
     re-evaluating a group on unchanged inputs rewrites the same values, evaluating one whose inputs
     are stale only touches values that are recomputed before anybody reads them (the caller marks
     the group valid only for the instances that asked)."""
-    W = 2 if pair else 1           # doubles per lane and slot
+    W = 2 if pair or wide else 1   # slot stride in tiles of 32 doubles (pair: two doubles per lane; wide: 64-lane tiles)
     ty = "double2" if pair else "double"
     insts = ("x", "y") if pair else ("",)
     tab, slot = pr.tab, pr.slot
@@ -270,7 +270,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
         if pair:
             head = [f"const double2 v{q}=*(const double2 *)(sc+{from_smem[q] * TILE * W});" for q in reads[k] if q in from_smem]
         else:
-            head = [f"const double v{q}=sc[{from_smem[q] * TILE}];" for q in reads[k] if q in from_smem]
+            head = [f"const double v{q}=sc[{from_smem[q] * TILE}];" for q in reads[k] if q in from_smem]   # (the cache is per warp)
         loads = [q for q in reads[k] if q not in from_smem]
         lines: List[str] = []
         tail: List[str] = []       # loaded operands that enter the cache: written at the end, when they have arrived
@@ -302,7 +302,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                 lines.append(f"*(double2 *)(sc+{keep_slot[i] * TILE * W})={both};" if pair else f"sc[{keep_slot[i] * TILE}]={both};")
                 stats["smem_stores"] += 1
             if i in to_hbm:
-                lines.append(f"*(double2 *)(mt+{int(slot[i]) * TILE * W})={both};" if pair else f"mt[{int(slot[i]) * TILE}]={both};")
+                lines.append(f"*(double2 *)(mt+{int(slot[i]) * TILE * W})={both};" if pair else f"mt[{int(slot[i]) * TILE * W}]={both};")
                 stores.add(int(slot[i]))
                 stats["stores"] += 1
             elif i not in keep_slot:
@@ -333,7 +333,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
             if pair:
                 src += [f"const double2 v{q}=*(const double2 *)(mt+{int(slot[q]) * TILE * W});" for q in loads]
             else:
-                src += [f"const double v{q}=mt[{int(slot[q]) * TILE}];" for q in loads]
+                src += [f"const double v{q}=mt[{int(slot[q]) * TILE * W}];" for q in loads]
             src += head
             # while this chunk's operands are in flight, pull the operands of the chunk `prefetch` positions ahead
             # into L2: its load phase then costs an L2 hit instead of an HBM round trip (no registers involved);
@@ -365,7 +365,7 @@ EMITTER_VERSION = 1
 TCM_ABI = 2
 
 
-def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, pair: int = 0) -> List[Tuple[str, str]]:
+def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, pair: int = 0, wide: int = 0) -> List[Tuple[str, str]]:
     """chunks of one copy function: sequential ``m[d]=m[s]`` (writeCfunctionpergroup.m:753-852)"""
     tab, slot = pr.tab, pr.slot
     c = pr.copies[name]
@@ -381,8 +381,8 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, 
             elif ts == it.I_2:
                 src = "2.0"
             else:
-                src = f"mt[{int(slot[s]) * TILE * (2 if pair else 1)}]"
-            lines.append(f"mt[{int(slot[d]) * TILE * (2 if pair else 1)}]={src};")
+                src = f"mt[{int(slot[s]) * TILE * (2 if pair or wide else 1)}]"
+            lines.append(f"mt[{int(slot[d]) * TILE * (2 if pair or wide else 1)}]={src};")
         lines += ["}", "}"]
         out.append((f"tcc{fn_id}_{k // max_pairs}", "\n".join(lines) + "\n"))
     return out
@@ -391,7 +391,7 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
                 warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1,
                 assume_global: int = 0, resident: int = 0, driver: str = "warp", scache: int = 0,
-                pair: int = 0):
+                pair: int = 0, wide: int = 0):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
     from .csparse import fingerprint
     from .tape import FN
@@ -407,7 +407,7 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         raise ValueError("scache: more than 227 KB of shared memory per CTA")
     for g in range(len(pr.groups)):
         fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global,
-                            barrier=int(lockstep > 1), scache=scache, pair=pair)
+                            barrier=int(lockstep > 1), scache=scache, pair=pair, wide=wide)
         funcs += fs
         group_calls.append([n for n, _ in fs])
         per_group.append(st)
@@ -419,10 +419,12 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
         raise ValueError("the lane-decoupled and work-queue drivers implement ipmPD_CSsolver only")
     for name, fid in fn_items(pr):
         if name in pr.copies:
-            fs = emit_copy(pr, fid, name, pair=pair)
+            fs = emit_copy(pr, fid, name, pair=pair, wide=wide)
             funcs += fs
             copy_calls[fid] = [n for n, _ in fs]
     # part files of roughly equal size (ptxas time is what we balance)
+    if wide and (pair or tiles != 1 or lockstep % 2 or driver != "warp"):
+        raise ValueError("wide needs the warp driver, one instance per lane and an even lockstep")
     if pair:                       # two interleaved instances per lane: the driver's tiles machinery with the
         if tiles not in (1, 2) or driver != "warp":     # pair layout (TC_PAIR) and 128-bit accesses
             raise ValueError("pair needs the warp driver (and implies tiles=2)")
@@ -439,6 +441,8 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
             '#define TC_TILE_LOOP _Pragma("unroll 1") for (int t = 0; t < TC_TILES; t++) if ((mask >> t) & 1u)\n'
             "#define TC_MT (m + (size_t)t * TC_TILE_STRIDE)\n"
             "#else\n#define TC_TILE_LOOP if (mask)\n#define TC_MT m\n#endif\n"
+            + ("// wide: tiles of 64 instances, m[tile][slot][64]; the lane's column pointer already holds its half\n"
+               "#define TC_WIDE 1\n" if wide else "")
             + ("#endif\n" if pair else "") +
             '#define TC_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))\n'
             "// per-lane software cache in shared memory (emitter option scache, plan_scache): warp w of the CTA owns\n"
@@ -539,8 +543,10 @@ __attribute__((visibility("default"))) int tcm_occupancy(void) {{
 }}
 // 1: scratchbook layout m[tile pair][slot][lane][2] (emitter option pair), 0: m[tile][slot][lane]
 __attribute__((visibility("default"))) int tcm_interleave(void) {{
-#ifdef TC_PAIR
+#if defined(TC_PAIR)
     return 1;
+#elif defined(TC_WIDE)
+    return 2;
 #else
     return 0;
 #endif

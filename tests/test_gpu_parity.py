@@ -102,6 +102,40 @@ def test_async_solve_and_two_handles_in_flight():
         o.close()
 
 
+def test_queued_batches_on_one_handle_with_async_outputs():
+    """set + tc_solve_async + tc_get_outputs_async twice on ONE handle without a host synchronisation in between
+    (two sets of pinned host buffers): both batches come back as the blocking calls deliver them"""
+    import torch
+    gen, args = generated("mpc_dcmotor")
+    batch = 900
+    ins = [problems.synthetic_inputs("mpc_dcmotor", gen, batch, seed=s) for s in (21, 22)]
+    want = []
+    for P, V in ins:
+        ref = _solve(gen, args, P, V, batch)
+        st, it, _ = ref.solve(args["mu0"], args["maxIter"], -1)
+        want.append((st, it, ref.getOutputs()))
+        ref.close()
+    sizes = [int(np.prod(s)) if s else 1 for _, s in gen.outputs]
+    obj = gen(batch)
+    bufs = [([torch.empty((batch, n), dtype=torch.float64).pin_memory() for n in sizes],
+             torch.empty(batch, dtype=torch.int32).pin_memory(), torch.empty(batch, dtype=torch.int32).pin_memory())
+            for _ in ins]
+    for (P, V), (outs, st, it) in zip(ins, bufs):
+        for n, _ in gen.parameters:
+            getattr(obj, "setP_" + n)(P[n])
+        for n, _ in gen.variables:
+            getattr(obj, "setV_" + n)(V[n])
+        obj.solve_async(st.numpy(), it.numpy(), args["mu0"], args["maxIter"])
+        obj.get_outputs_ptrs([t.data_ptr() for t in outs], device=False, sync=False)
+    obj.synchronize()
+    for (st0, it0, y0), (outs, st, it) in zip(want, bufs):
+        assert np.array_equal(st.numpy(), st0) and np.array_equal(it.numpy(), it0)
+        ys = list(y0.values()) if isinstance(y0, dict) else list(y0)
+        for a, b, (_, shape) in zip(outs, ys, gen.outputs):        # same unpacking as BatchedSolver.getOutputs
+            assert np.array_equal(a.numpy().T.reshape(tuple(shape) + (batch,), order="F"), b)
+    obj.close()
+
+
 def test_tiles_option_is_bit_identical():
     """two instances per lane (emitter option tiles=2) walk the same code: identical results"""
     gen, args = generated("sls")
@@ -119,13 +153,13 @@ def test_tiles_option_is_bit_identical():
 
 
 @pytest.mark.parametrize("opts", [dict(pair=1, max_loads=14), dict(scache=24), dict(pair=1, max_loads=14, scache=12),
-                                  dict(lockstep=6, warps_per_sm=24), dict(prefetch=0)],
-                         ids=["pair", "scache", "pair+scache", "lockstep6", "noprefetch"])
+                                  dict(lockstep=6, warps_per_sm=24), dict(prefetch=0), dict(wide=1)],
+                         ids=["pair", "scache", "pair+scache", "lockstep6", "noprefetch", "wide"])
 @pytest.mark.parametrize("name,batch", [("sls", 1000), ("mpc_dcmotor", 700)])
 def test_layout_options_are_bit_identical(name, batch, opts):
     """emitter options that change where values live, not what is computed: `pair` (two instances per lane in
     interleaved columns, 128-bit loads and stores; the set/gather/compaction kernels follow the layout through
-    tc_device_image::ilv), `scache` (per-lane software cache in shared memory, offline Belady plan), CTAs of 6
+    tc_device_image::ilv), `wide` (tiles of 64 instances: two lockstep warps share 512-byte segments), `scache` (per-lane software cache in shared memory, offline Belady plan), CTAs of 6
     lockstep warps, no L2 prefetch -- same status, iterations and outputs as the default module, on a ragged batch,
     and the same again after a set + re-solve on the same handle (stale lazy-evaluation state of the partner)"""
     gen, args = generated(name)
