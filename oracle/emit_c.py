@@ -202,12 +202,18 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
             w(f"#define {k} {v:e}\n" if k in _DOUBLE_DEFINES else f"#define {k} {v}\n")
     w(f"static SCRATCHBOOK_TYPE scratchbook[{max(pr.n_slots, 1)}];\n")
     w(f"static int groupStatus[{max(len(pr.groups), 1)}];\n")
+    # variant "count": executions of every dependency group -- the counters behind the reference's profiling option
+    # (writeCfunctionpergroup.m:149-177,481-492), which examples/flops.m:94-99 turns into flops per solve
+    w(f"#ifdef ORACLE_COUNT\nstatic long long oracle_group_count[{max(len(pr.groups), 1)}];\n"
+      f"EXPORT void oracle_group_counts(long long *out, int reset) {{ for (int g=0; g<{len(pr.groups)}; g++) "
+      "{ out[g]=oracle_group_count[g]; if (reset) oracle_group_count[g]=0; } }\n#endif\n")
     for g, members in enumerate(pr.groups):
         chunks = [members[k:k + MAX_PER_FUNCTION] for k in range(0, len(members), MAX_PER_FUNCTION)]
         for c, chunk in enumerate(chunks):
             body = ref.statements(chunk) if ref else "".join(statement(tab, i, slot) for i in chunk)
             w(f"static void group{g}_{c}(void) {{\n  SCRATCHBOOK_TYPE *m=scratchbook;\n{body}}}\n")
-        w(f"static void group{g}(void) {{\n" + "".join(f"  group{g}_{c}();\n" for c in range(len(chunks))) + "}\n")
+        w(f"static void group{g}(void) {{\n#ifdef ORACLE_COUNT\n  oracle_group_count[{g}]++;\n#endif\n"
+          + "".join(f"  group{g}_{c}();\n" for c in range(len(chunks))) + "}\n")
 
     for s in pr.sets.values():
         fname = f"{gen.classname}_set_{s.name[5:]}" if s.kind != "solver" else s.name

@@ -59,8 +59,8 @@ class Oracle:
             from tenscalc_b200.csparse import fingerprint
             tag = gen.classname + "_" + fingerprint(gen.problem)[:10]
         self.opt = opt
-        if variant not in ("", "crpow"):
-            raise ValueError("variant must be '' or 'crpow' (libm-sensitivity probe, see emit_c.py)")
+        if variant not in ("", "crpow", "count"):
+            raise ValueError("variant must be '', 'crpow' (libm-sensitivity probe) or 'count' (group execution counters)")
         self.variant = variant
         self.so = os.path.join(OUT, f"{tag}_{kind}{opt.replace('-', '_').replace(' ', '').replace('=', '')}"
                                     f"{'_' + variant if variant else ''}.so")
@@ -77,6 +77,8 @@ class Oracle:
             f.write(src)
         # plain gcc, no -march/-ffast-math: the reference is built the same way by CmexTools
         extra = ["-DORACLE_CRPOW", "-mfma", "-ffp-contract=off"] if self.variant == "crpow" else []
+        if self.variant == "count":
+            extra = ["-DORACLE_COUNT"]
         subprocess.check_call(["gcc"] + self.opt.split() + extra + ["-w", "-shared", "-fPIC", "-fvisibility=hidden",
                                cfile, "-o", self.so, "-lm"])
         return self.so
@@ -113,3 +115,10 @@ class Oracle:
                              ae.ctypes.data_as(dp), status.ctypes.data_as(ip), it.ctypes.data_as(ip),
                              Y.ctypes.data_as(dp), sec.ctypes.data_as(dp))
         return status, it, unpack_outputs(self.gen, Y), sec
+
+    def group_counts(self, reset: bool = True) -> np.ndarray:
+        """variant 'count': how often every dependency group ran since the last reset"""
+        lib = self.load()
+        out = np.zeros(max(len(self.gen.problem.groups), 1), dtype=np.int64)
+        lib.oracle_group_counts(out.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), ctypes.c_int(int(reset)))
+        return out[:len(self.gen.problem.groups)]

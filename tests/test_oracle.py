@@ -123,6 +123,42 @@ def test_equilibrium_reduced_newton_matrix_matches_large(name, kw):
         assert np.median(np.abs(out_l[k] - out_s[k]).reshape(-1, out_l[k].shape[-1]).max(0)) < 1e-6
 
 
+@pytest.mark.parametrize("N,anchor", [(30, 19621), (60, 113946)])         # (100, 449246) holds too: 529 542, 3 min
+def test_flops_per_solve_against_the_reference_anchors(N, anchor):
+    """examples/flops.m:29-42 records the flops of ONE solve of min x'Ax-b'x (dense N x N, no constraints) as the
+    reference's profiling counters see them: per-group operation counts (instructionsTableUTHash.c:816-832) times
+    group executions.  The same product from the restated front end (metrics.group_tables x the oracle's execution
+    counters, variant 'count') on a positive definite A: one factorisation per solve, the LDL' group within 11 % of
+    N^3/3, and the total 18-26 % ABOVE the reference's figure -- the restated gradient/Hessian/residual code of this
+    problem is not MATLAB's instruction for instruction (DESIGN.md section 4 says so; this test keeps the number honest)"""
+    from oracle.oracle import Oracle
+    from tenscalc_b200 import metrics, tensor as T
+    from tenscalc_b200.optimize import cmex2optimizeCS
+    from tenscalc_b200.tensor import Tvariable
+    T.clear()
+    x, A, b = Tvariable("x", [N]), Tvariable("A", [N, N]), Tvariable("b", [N])
+    gen = cmex2optimizeCS(classname="tmp_flops", objective=(x @ A) @ x - b @ x, optimizationVariables=[x],
+                          constraints=[], outputExpressions=[(x @ A) @ x - b @ x, x], parameters=[A, b])
+    rng = np.random.default_rng(0)
+    B = 4
+    M = rng.standard_normal((N, N, B))
+    P = {"A": np.einsum("ijb,kjb->ikb", M, M) / N + np.eye(N)[:, :, None], "b": rng.standard_normal((N, B))}
+    o = Oracle(gen, "port", variant="count")
+    o.group_counts()
+    st, it, out, _ = o.solve_batch(P, {"x": np.ones((N, B))}, 1.0, 30)           # flops.m:62-80
+    cnt = o.group_counts()
+    assert (st == 0).all() and (it == 2).all()
+    xs = out["y2"]
+    for k in range(B):                                                           # flops.m:88: x = inv(A+A')*b
+        assert np.abs(np.linalg.solve(P["A"][:, :, k] + P["A"][:, :, k].T, P["b"][:, k]) - xs[:, k]).max() < 1e-8
+    fl = metrics.group_tables(gen.problem)["flops"]
+    ldl = int(np.argmax(fl))
+    assert cnt[ldl] == B                                                         # one factorisation per solve
+    assert N ** 3 / 3 <= fl[ldl] <= 1.11 * N ** 3 / 3
+    per_solve = float((fl * cnt).sum()) / B
+    assert 1.15 * anchor < per_solve < 1.27 * anchor
+
+
 def test_minmax_port_solves_the_box_game():
     """ipmPDminmax_CSsolver (PARITY UNPINNED, oracle/ipm_driver_minmax_port.c) on cases 5 / 5.5 of
     examples/minmaxTest.m: min_u max_d |u+d+a|^2-2|d+2|^2 on -2<=u<=2, -1<=d<=1 has d=-1, u=clip(1-a,-2,2)"""
