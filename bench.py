@@ -379,8 +379,10 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
     except (OSError, StopIteration):
         avail = 0
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
-    nbuf = 2 if with_e2e and 2 * depth * set_bytes * local_world < 0.4 * avail else 1
-    nsets = depth * nbuf if with_e2e else 1
+    max_sets = max(1, int(0.35 * avail // (set_bytes * local_world))) if avail else depth
+    nbuf = 2 if max_sets >= 2 * depth else 1
+    e2e_depth = min(depth, max_sets)                 # short of host memory: fewer handles take part in this arm
+    nsets = e2e_depth * nbuf if with_e2e else 1
     h_outs = [[torch.empty((B, n), dtype=torch.float64).pin_memory() for n in out_sizes] for _ in range(nsets)]
     h_stats = [(torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
                for _ in range(nsets)]
@@ -395,13 +397,13 @@ def _measure(args, name, gen, sargs, B, K, W, rank, local_rank, world, barrier, 
     e2e_done = {}
 
     def e2e_submit(i):         # everything of step i is enqueued on its handle's stream; nothing blocks
-        o = objs[i % depth]
+        o = objs[i % e2e_depth]
         for k, t in h_in.items():
             o.set_packed(k, t.numpy())
         o.solve_async(h_stats[i % nsets][0].numpy(), h_stats[i % nsets][1].numpy(), mu0, maxIter)
         o.get_outputs_ptrs([t.data_ptr() for t in h_outs[i % nsets]], device=False, sync=False)
         e2e_done[i] = torch.cuda.Event()
-        e2e_done[i].record(exts[i % depth])
+        e2e_done[i].record(exts[i % e2e_depth])
 
     def e2e_collect(i):        # blocks until step i is complete and its results are in host memory
         e2e_done.pop(i).synchronize()
