@@ -137,7 +137,8 @@ def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0,
     import shutil
 
     # register budget of the chunk functions: the kernel runs warps_per_sm warps on the 64K-register SM
-    reg_budget = min(255, 65536 // (32 * int(emit_opts.get("warps_per_sm", 8))) // 8 * 8)
+    # (registers are allocated to warps in groups of four: 14 warps/SM cost what 16 do)
+    reg_budget = min(255, 65536 // (32 * ((int(emit_opts.get("warps_per_sm", 8)) + 3) // 4 * 4)) // 8 * 8)
     flags = MODULE_FLAGS + [f"-maxrregcount={reg_budget}"]
 
     def compile_one(name: str) -> str:
