@@ -118,6 +118,9 @@ def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0,
     so = module_path(gen, **emit_opts)
     if not force and os.path.exists(so):
         return so
+    # fmad=1 (experiment, profiles/r03u_*): let nvcc contract a*b+c into DFMA.  NOT the arithmetic contract of the
+    # product -- the reference's x86-64 build rounds products and sums separately, and so does the default module
+    fmad = int(emit_opts.get("fmad", 0))
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         raise RuntimeError(f"compiled module {so} is missing and nvcc is not available to build it")
@@ -139,7 +142,7 @@ def build_module(gen, force: bool = False, verbose: bool = False, jobs: int = 0,
     # register budget of the chunk functions: the kernel runs warps_per_sm warps on the 64K-register SM
     # (registers are allocated to warps in groups of four: 14 warps/SM cost what 16 do)
     reg_budget = min(255, 65536 // (32 * ((int(emit_opts.get("warps_per_sm", 8)) + 3) // 4 * 4)) // 8 * 8)
-    flags = MODULE_FLAGS + [f"-maxrregcount={reg_budget}"]
+    flags = [("-fmad=true" if fmad and f == "-fmad=false" else f) for f in MODULE_FLAGS] + [f"-maxrregcount={reg_budget}"]
 
     def compile_one(name: str) -> str:
         obj = os.path.join(src_dir, name[:-3] + ".o")

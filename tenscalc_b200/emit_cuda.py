@@ -391,8 +391,9 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
                 warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1,
                 assume_global: int = 0, resident: int = 0, driver: str = "warp", scache: int = 0,
-                pair: int = 0, wide: int = 0):
-    """returns ({file name: source}, stats) of the CUDA module of one generated solver"""
+                pair: int = 0, wide: int = 0, fmad: int = 0):
+    """returns ({file name: source}, stats) of the CUDA module of one generated solver (``fmad`` is a compiler flag
+    of build.build_module, an experiment: it does not change the emitted source)"""
     from .csparse import fingerprint
     from .tape import FN
     pr: CompiledProblem = gen.problem
