@@ -8,6 +8,7 @@ from concurrent.futures import ProcessPoolExecutor
 AFFINE = {"algorithm": "ipmPD_CS", "skipAffine": False}           # Mehrotra predictor (ipmPD_CSsolver.c:576-665, ipmPD_CS.m)
 AFFINE_SMALL = {**AFFINE, "smallerNewtonMatrix": True}            # + reduced Newton matrix (ipmPD_CS.m:242-351)
 CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}), ("isa_probe", {}),
+           ("isa_probe", {"cw": True}),                            # user-defined componentwise function (I_componentwise)
            ("mpc_quadcopter", {"T_": 20, "useInertia": True}),    # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
            ("sls", AFFINE), ("mpc_dcmotor", AFFINE), ("mpc_dcmotor", AFFINE_SMALL),
            ("mpc_quadcopter", {"T_": 20, **AFFINE})]

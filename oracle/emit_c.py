@@ -106,6 +106,8 @@ def statement(tab: it.InstructionTable, i: int, slot: np.ndarray) -> str:
         it.I_ddsrelu: f"1/(2+exp(-{x})+exp({x}))", it.I_relu: f"({x}>0)?{x}:0",
         it.I_heaviside: f"({x}>0)?1:0",
     }
+    if t == it.I_componentwise:                                               # :1333-1345
+        return f"\t{r}=" + it.componentwise_text(p, x) + ";\n"
     if t in unary:
         return f"\t{r}={unary[t]};\n"
     raise NotImplementedError(it.OPNAMES.get(t, str(t)))

@@ -114,6 +114,12 @@ def eval_instruction(tab: it.InstructionTable, i: int, v: Dict[int, np.ndarray],
     if t in _UNARY:
         with np.errstate(all="ignore"):
             return _UNARY[t](v[o[0]])
+    if t == it.I_componentwise:                                    # :1333-1345, through the function's Python form
+        f = tab.cw_funcs.get(it.componentwise_text(p, "%s"), (None, None))[0]
+        if f is None:
+            raise NotImplementedError("componentwise without a Python form")
+        with np.errstate(all="ignore"):
+            return np.vectorize(f, otypes=[np.float64])(np.broadcast_to(v[o[0]], (B,)))
     raise NotImplementedError(it.OPNAMES.get(t, str(t)))
 
 

@@ -109,6 +109,20 @@ class Differentiator:
             else:
                 dt = tab.unary_derivative_type(t)
                 contribute(1, o, (tab.unary(dt, o),))
+        elif t == it.I_componentwise:
+            # chain rule with the derivative the user supplied (Tcalculus.m:1836-1880), applied to the scalar operand
+            (o,) = ops
+            text = it.componentwise_text(tab.params[x], "%s")
+            d = tab.cw_funcs.get(text, (None, None))[1]
+            if d is None:
+                raise NotImplementedError(f"componentwise '{text}': no derivative was given")
+            from .tensor import Tcalculus, _obj
+            e = _obj(())
+            e[()] = o
+            dy = Tcalculus._lift(d(Tcalculus(e)))
+            if dy.numel() != 1:
+                raise ValueError(f"componentwise '{text}': the derivative of a scalar must be a scalar")
+            contribute(1, o, (dy.flat()[0],))
         else:
             raise NotImplementedError(f"derivative of {it.OPNAMES.get(t, t)} requested")
         out = {}

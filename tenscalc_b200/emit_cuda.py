@@ -87,6 +87,10 @@ def expression(t: int, p: Sequence[float], o: List[str], r: str) -> str:
         for k in range(0, len(o), 2):
             s += f" if ({o[k + 1]}<0) {{const double x_=-{o[k]}/{o[k + 1]}; if ({r}>x_) {r}=x_;}}"
         return s
+    if t == it.I_componentwise:                                               # :1333-1345
+        # the user's C text with the operand at every placeholder; on the device it is compiled as CUDA C, so it
+        # may call what <cmath> offers there (the text is the user's: its arithmetic is theirs)
+        return f"const double {r}=" + it.componentwise_text(p, f"({o[0]})") + ";"
     x = o[0] if o else ""
     unary = {                                                                 # :1347-1539
         it.I_round: f"round({x})", it.I_ceil: f"ceil({x})", it.I_floor: f"floor({x})",
@@ -147,6 +151,121 @@ def chunk_group(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_
     return chunks
 
 
+ROLLABLE = (it.I_sum, it.I_sumprod, it.I_div)      # the types writeCinstructionsC emits as for(;;) loops
+MAX_DELTA_OPERANDS = 10                            # instructionsTableUTHash.c:784
+
+
+def rolled_runs(pr: CompiledProblem, members: Sequence[int], min_len: int) -> List[Tuple[int, int]]:
+    """[(position in ``members``, count)] of the runs the reference emitter rolls into ``for`` loops
+    (instructionsTableUTHash.c:881-944): consecutive instructions of equal type, parameter vector and
+    operand count (at most 10 operands) whose result slot and every operand slot advance by constant
+    strides; scanned greedily from every instruction, rolled when the run holds at least ``min_len``
+    (``minInstructions4loop``, default 50) instructions of type sum, sumprod or div."""
+    tab, slot = pr.tab, pr.slot
+    n = len(members)
+
+    def same_shape(a: int, b: int) -> bool:
+        return (tab.types[a] == tab.types[b] and len(tab.operands[a]) == len(tab.operands[b])
+                and list(tab.params[a]) == list(tab.params[b]))
+
+    runs: List[Tuple[int, int]] = []
+    i = 0
+    while i < n:
+        a = members[i]
+        nxt = i + 1
+        if nxt < n and len(tab.operands[a]) <= MAX_DELTA_OPERANDS and same_shape(a, members[nxt]):
+            b = members[nxt]
+            d_res = int(slot[b]) - int(slot[a])
+            d_ops = [int(slot[y]) - int(slot[x]) for x, y in zip(tab.operands[a], tab.operands[b])]
+            nxt += 1
+            while nxt < n:
+                prev, c = members[nxt - 1], members[nxt]
+                if int(slot[c]) - int(slot[prev]) != d_res or not same_shape(a, c):
+                    break
+                if [int(slot[y]) - int(slot[x]) for x, y in zip(tab.operands[prev], tab.operands[c])] != d_ops:
+                    break
+                nxt += 1
+        if tab.types[a] in ROLLABLE and nxt - i >= min_len:
+            runs.append((i, nxt - i))
+            i = nxt
+        else:
+            i += 1
+    return runs
+
+
+def _device_rollable(pr: CompiledProblem, run: Sequence[int]) -> bool:
+    """a run becomes a device loop when every operand position is either the SAME constant in all its
+    instructions (an immediate) or a scratchbook value in all of them (constants live in no scratchbook)"""
+    tab = pr.tab
+    const_types = (it.I_load, it.I_2)
+    first = tab.operands[run[0]]
+    for i in run[1:]:
+        for x, y in zip(first, tab.operands[i]):
+            if (tab.types[x] in const_types or tab.types[y] in const_types) and x != y:
+                return False
+    return True
+
+
+def chunk_group_rolled(pr: CompiledProblem, members: Sequence[int], max_refs: int, max_loads: int,
+                       roll: int) -> Tuple[List[List[int]], Set[int]]:
+    """``chunk_group`` with every rolled run (``rolled_runs`` of at least ``roll`` instructions) as a chunk of its
+    own: (chunks, indices of the rolled chunks)"""
+    chunks: List[List[int]] = []
+    rolled: Set[int] = set()
+    pos = 0
+    for start, count in rolled_runs(pr, members, roll) if roll else []:
+        run = list(members[start:start + count])
+        if not _device_rollable(pr, run):
+            continue
+        if start > pos:
+            chunks += chunk_group(pr, members[pos:start], max_refs, max_loads)
+        rolled.add(len(chunks))
+        chunks.append(run)
+        pos = start + count
+    if pos < len(members) or not chunks:
+        chunks += chunk_group(pr, members[pos:], max_refs, max_loads)
+    return chunks, rolled
+
+
+def emit_rolled(pr: CompiledProblem, run: Sequence[int], W: int) -> Tuple[List[str], int]:
+    """statements of one rolled run: ``for`` over the instructions of the run, slot of every operand and of the
+    result = first slot + counter x stride.  Runs without a loop-carried value (no instruction of the run reads
+    a slot the run writes) fetch the operands of ``U`` iterations back to back before computing them (one memory
+    round trip per ``U`` instructions, like a chunk); the others run strictly in the reference's order."""
+    tab, slot = pr.tab, pr.slot
+    const_types = (it.I_load, it.I_2)
+    a, n = run[0], len(run)
+    t, p = tab.types[a], tab.params[a]
+    ops = tab.operands[a]
+    d_res = int(slot[run[1]]) - int(slot[a])
+    d_ops = [int(slot[y]) - int(slot[x]) for x, y in zip(ops, tab.operands[run[1]])]
+    var = [j for j, q in enumerate(ops) if tab.types[q] not in const_types]
+    written = {int(slot[i]) for i in run}
+    carried = any(int(slot[q]) in written for i in run for q in tab.operands[i] if tab.types[q] not in const_types)
+    U = 1 if carried else max(1, min(8, 48 // max(len(var), 1)))
+
+    def addr(s0: int, d: int) -> str:
+        return f"mt[({s0}+(c0+u)*({d}))*{TILE * W}]"
+
+    o: List[str] = []
+    for j, q in enumerate(ops):
+        if tab.types[q] == it.I_load:
+            o.append("(" + _lit(tab.params[q][0]) + ")")
+        elif tab.types[q] == it.I_2:
+            o.append("2.0")
+        else:
+            o.append(f"x_[u][{var.index(j)}]")
+    lines = [f"// rolled run: {n} x {it.OPNAMES.get(t, t)} (instructionsTableUTHash.c:881-944)"
+             + (", loop-carried" if carried else ""),
+             f'_Pragma("unroll 1") for (int c0 = 0; c0 < {n}; c0 += {U}) {{',
+             f"double x_[{U}][{max(len(var), 1)}];",
+             f'_Pragma("unroll") for (int u = 0; u < {U}; u++) if (c0 + u < {n}) {{']
+    lines += [f"x_[u][{k}]={addr(int(slot[ops[j]]), d_ops[j])};" for k, j in enumerate(var)]
+    lines += ["}", f'_Pragma("unroll") for (int u = 0; u < {U}; u++) if (c0 + u < {n}) {{',
+              expression(t, p, o, "r_"), f"{addr(int(slot[a]), d_res)}=r_;", "}", "}"]
+    return lines, len(var)
+
+
 def plan_scache(reads: List[List[int]], makes: List[List[int]], ext: Set[int], capacity: int):
     """Offline allocation of a per-lane shared-memory cache of ``capacity`` doubles for one group.
 
@@ -203,8 +322,12 @@ def plan_scache(reads: List[List[int]], makes: List[List[int]], ext: Set[int], c
 def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
                max_loads: int = 96, prefetch: int = 1, merge: int = 1,
                assume_global: int = 0, barrier: int = 0, scache: int = 0,
-               pair: int = 0, wide: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
+               pair: int = 0, wide: int = 0, roll: int = 0) -> Tuple[List[Tuple[str, str]], Dict[str, int]]:
     """[(function name, CUDA source)] of the chunks of group g, plus traffic statistics.
+
+    ``roll`` > 0: runs of at least ``roll`` strided repeats of one sum / sumprod / div instruction become
+    device loops (``rolled_runs``: the reference's loop rolling, ``minInstructions4loop``), each a chunk of its
+    own that reads and writes the scratchbook directly.
 
     ``pair``: every lane carries TWO instances whose scratchbook columns are interleaved
     (``m[tile pair][slot][lane][2]``): a chunk runs the group on both -- one 128-bit load or store
@@ -218,7 +341,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
     insts = ("x", "y") if pair else ("",)
     tab, slot = pr.tab, pr.slot
     members = pr.groups[g]
-    chunks = chunk_group(pr, members, max_refs, max_loads)
+    chunks, rolled = chunk_group_rolled(pr, members, max_refs, max_loads, roll)
     chunk_of = {i: k for k, ch in enumerate(chunks) for i in ch}
     const_types = (it.I_load, it.I_2)
     skip_types = (it.I_set, it.I_load, it.I_2)
@@ -252,7 +375,7 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
         plan, to_hbm = plan_scache(reads, makes, ext, scache)
     else:
         plan, to_hbm = [({}, []) for _ in chunks], ext | cross
-    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0, smem_loads=0, smem_stores=0)
+    stats = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0, smem_loads=0, smem_stores=0, rolled=0)
     bodies = []                    # per chunk: (name, HBM load slots in issue order, store slots, statements)
     def ld(q: int, e: str) -> str:          # a fetched operand of instance e: the vector's component
         return f"v{q}.{e}" if pair else f"v{q}"
@@ -262,6 +385,13 @@ def emit_group(pr: CompiledProblem, g: int, ext: Set[int], max_refs: int = 1536,
 
     for k, ch in enumerate(chunks):
         name = f"tcg{g}_{k}"
+        if k in rolled:                       # a loop over the run: operands from / results to the scratchbook
+            body, nvar = emit_rolled(pr, ch, W)
+            stats["loads"] += nvar * len(ch)
+            stats["stores"] += len(ch)
+            stats["rolled"] += len(ch)
+            bodies.append((name, [], {int(slot[i]) for i in ch}, [], body))
+            continue
         from_smem, to_smem = plan[k]
         keep_slot = dict(to_smem)
         fetched = set(reads[k])
@@ -391,7 +521,7 @@ def emit_copy(pr: CompiledProblem, fn_id: int, name: str, max_pairs: int = 192, 
 def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int = 400_000, lockstep: int = 1,
                 warps_per_sm: int = 8, prefetch: int = 1, merge: int = 24, divcall: int = 0, tiles: int = 1,
                 assume_global: int = 0, resident: int = 0, driver: str = "warp", scache: int = 0,
-                pair: int = 0, wide: int = 0, fmad: int = 0):
+                pair: int = 0, wide: int = 0, fmad: int = 0, roll: int = 0):
     """returns ({file name: source}, stats) of the CUDA module of one generated solver (``fmad`` is a compiler flag
     of build.build_module, an experiment: it does not change the emitted source)"""
     from .csparse import fingerprint
@@ -400,15 +530,17 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
     ext = external_values(pr)
     funcs: List[Tuple[str, str]] = []
     group_calls: List[List[str]] = []
-    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0, smem_loads=0, smem_stores=0)
+    total = dict(loads=0, stores=0, reg_reads=0, reg_only=0, prefetches=0, smem_loads=0, smem_stores=0, rolled=0)
     per_group = []
+    if roll and (scache or pair):
+        raise ValueError("roll: rolled runs address the plain scratchbook (no scache, no pair)")
     if scache and ((tiles != 1 and not pair) or resident or driver != "warp"):
         raise ValueError("scache needs the warp driver with one instance per lane (or pair) and no `resident` cap")
     if scache * 8 * TILE * lockstep * (2 if pair else 1) > 227 * 1024:
         raise ValueError("scache: more than 227 KB of shared memory per CTA")
     for g in range(len(pr.groups)):
         fs, st = emit_group(pr, g, ext, max_refs, max_loads, prefetch, merge, assume_global,
-                            barrier=int(lockstep > 1), scache=scache, pair=pair, wide=wide)
+                            barrier=int(lockstep > 1), scache=scache, pair=pair, wide=wide, roll=roll)
         funcs += fs
         group_calls.append([n for n, _ in fs])
         per_group.append(st)

@@ -72,6 +72,7 @@ I_dsrelu = 45
 I_ddsrelu = 46
 I_relu = 47
 I_heaviside = 48
+I_componentwise = 50   # user-defined scalar function given as C text (instructionsTableTypes.h:53; 49 = I_zero, never emitted)
 
 OPNAMES = {v: k for k, v in list(globals().items()) if k.startswith("I_")}
 
@@ -143,6 +144,23 @@ _UNARY_DERIV = {
 MAX_TERMS_PERLINE = 100
 
 
+def _cw_split(cfun: str):
+    """characters of a componentwise C text, None at every ``%s``"""
+    out = []
+    parts = cfun.split("%s")
+    for k, part in enumerate(parts):
+        out += list(part)
+        if k + 1 < len(parts):
+            out.append(None)
+    return out
+
+
+def componentwise_text(params, operand: str) -> str:
+    """C expression of an ``I_componentwise`` instruction: its characters with ``operand`` at every 0
+    (instructionsTableUTHash.c:1337-1343)"""
+    return "".join(operand if c == 0 else chr(int(c)) for c in params)
+
+
 def sumprod_lines(m: int, o):
     """The emitted statement(s) of ``I_sumprod [m, s]`` over operand expressions ``o``: one string per LINE of
     the reference's C (instructionsTableUTHash.c:1007-1029).  The emitter counts ``m`` factors per product and
@@ -165,6 +183,7 @@ class InstructionTable:
         self.names: Dict[int, str] = {}  # I_set only: debugging label
         self._index: Dict[tuple, int] = {}
         self.sqrt_by_division = True   # see differentiate.Differentiator
+        self.cw_funcs: Dict[str, tuple] = {}   # componentwise C text -> (Python form, derivative)
         self.split_long = True     # chunk sums of products longer than one emitted line (see MAX_TERMS_PERLINE)
 
     # -- raw access --------------------------------------------------------------
@@ -340,6 +359,25 @@ class InstructionTable:
         return self.append_unique(I_div, (), (a, b))
 
     # -- unary functions ---------------------------------------------------------
+    def componentwise(self, cfun: str, x: Id, pyfun=None, derivative=None) -> Id:
+        """``I_componentwise`` (sparsity_componentwise.m:33-35): the user's C text ``cfun`` with every ``%s``
+        standing for the operand; the parameter vector holds the characters of the text, 0 at every operand
+        position (the form writeCinstructionsC prints, instructionsTableUTHash.c:1333-1345).  ``pyfun`` (a
+        Python callable of a float) folds constants, ``derivative`` (a callable of a Tcalculus returning a
+        Tcalculus) is the chain rule's factor; both are remembered per C text."""
+        if "%s" not in cfun:
+            raise ValueError("componentwise: the C text must hold %s where the operand goes")
+        if pyfun is not None or derivative is not None or cfun not in self.cw_funcs:
+            old = self.cw_funcs.get(cfun, (None, None))
+            self.cw_funcs[cfun] = (pyfun or old[0], derivative or old[1])
+        if self.is_const(x):   # (structural zeros included: the reference fills them with I_load 0 when f(0) is not 0)
+            f = self.cw_funcs[cfun][0]
+            if f is None:
+                raise ValueError("componentwise of a constant needs the Python form of the function")
+            return self.const(float(f(self.const_value(x))))
+        params = tuple(0.0 if part is None else float(ord(part)) for part in _cw_split(cfun))
+        return self.append_unique(I_componentwise, params, (x,))
+
     def unary(self, typ: int, x: Id) -> Id:
         assert typ in UNARY_TYPES or typ == I_2
         if typ == I_2:
@@ -457,6 +495,8 @@ class InstructionTable:
             return self.div(new_ops[0], new_ops[1])
         if t in UNARY_TYPES:
             return self.unary(t, new_ops[0])
+        if t == I_componentwise:
+            return self.componentwise(componentwise_text(p, "%s"), new_ops[0])
         if t == I_plus_sqr:
             return self.plus_sqr(new_ops)
         if t == I_plus_abs:

@@ -153,13 +153,23 @@ def mpc_quadcopter(T_: int = 100, **opts) -> Tuple[GeneratedSolver, dict]:
     return gen, dict(mu0=1e-3, maxIter=1000)
 
 
-def isa_probe(N: int = 60, **opts) -> Tuple[GeneratedSolver, dict]:
+def _cw_sin(x):
+    """sin as a user-defined componentwise function with first and second derivative (Tcalculus.m:1851-1853)"""
+    import math
+    from .tensor import componentwise
+    return componentwise(x, math.sin, "sin(%s)",
+                         lambda z: componentwise(z, math.cos, "cos(%s)", lambda w: -componentwise(w, math.sin, "sin(%s)")))
+
+
+def isa_probe(N: int = 60, cw: bool = False, **opts) -> Tuple[GeneratedSolver, dict]:
     """Not a reference example: a small smooth bounded problem whose cost, gradient and Hessian together
     contain every unary opcode of the scalar ISA (lib/instructionTypes.m:8-117, C forms
     instructionsTableUTHash.c:1347-1539) and sums of products longer than one emitted line (:1019-1026,
     ``split_long`` off), so that the parity tests execute all of them on the device against the reference's
     own emitter.  Non-differentiable opcodes (abs, sign, round, ceil, floor, relu, heaviside) act on
-    parameters only."""
+    parameters only.  ``cw=True`` writes the sine term as a user-defined ``componentwise`` function with its two
+    derivatives (the example of lib/@Tcalculus/Tcalculus.m:1851-1853: ``I_componentwise`` instructions carrying
+    the C texts ``sin(%s)`` / ``cos(%s)``) -- the same problem, so the same iterates."""
     from .tensor import _compose, abs_, atan, cos, cube, exp, log, relu, sin, sqr, srelu
     from . import itable as it
     T.clear()
@@ -181,7 +191,7 @@ def isa_probe(N: int = 60, **opts) -> Tuple[GeneratedSolver, dict]:
              C[3] * X[3] - log(X[3] + 3),
              cube(X[4]) + 10 * sqr(X[4] - C[4]),
              C[5] * X[5] - cos(X[5]),
-             sin(X[6]) + 2 * sqr(X[6]),
+             (_cw_sin(X[6]) if cw else sin(X[6])) + 2 * sqr(X[6]),
              C[7] * X[7] - sqrt(X[7] + 3),
              1 / (X[8] + 3) + sqr(X[8]),
              sqr(X[9]) * (1 + step)]

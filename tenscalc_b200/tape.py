@@ -241,6 +241,9 @@ def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
             c.append([OP_CLP, F_INIT if k == 0 else 0, opw[k], opw[k + 1]])
     elif t in it.UNARY_TYPES:
         c.append([OP_UNARY + t, 0, opw[0], N])
+    elif t == it.I_componentwise:
+        raise NotImplementedError("I_componentwise is user C text: it needs the compiled back end (backend='compiled'), "
+                                  "the tape interpreter cannot run it")
     else:
         raise NotImplementedError(it.OPNAMES.get(t, str(t)))
     c[-1][1] |= F_END

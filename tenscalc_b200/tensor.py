@@ -303,6 +303,30 @@ def srelu(x):
     return _compose(x, it.I_srelu)
 
 
+def componentwise(x, fun, cfun: str, derivative1=None, derivative2=None) -> Tcalculus:
+    """``y=componentwise(x,fun,cfun,derivative1,derivative2)`` (lib/@Tcalculus/Tcalculus.m:1836-1880): a user-defined
+    scalar function applied entry by entry.  ``fun`` is its Python form (constant folding, structural zeros),
+    ``cfun`` the C text with ``%s`` for the operand that the back ends compile (``I_componentwise``),
+    ``derivative1(x)`` returns the derivative as a Tcalculus expression (which may itself be a
+    ``componentwise`` carrying ``derivative2`` as ITS derivative, as in the reference's example
+    ``componentwise(x,@sin,'sin(%s)',@(x)componentwise(x,@cos,'cos(%s)',@(x)-componentwise(x,@sin,'sin(%s)')))``)."""
+    if not callable(fun):
+        raise TypeError("componentwise 2nd argument must be a function")
+    tab = table()
+    d1 = derivative1
+    if derivative1 is not None and derivative2 is not None:
+        def d1(z, _d1=derivative1, _d2=derivative2):   # the derivative's own derivative rides on its instruction
+            y = _d1(z)
+            for i in Tcalculus._lift(y).flat():
+                if i is not None and tab.types[i] == it.I_componentwise:
+                    text = it.componentwise_text(tab.params[i], "%s")
+                    f0, dd = tab.cw_funcs.get(text, (None, None))
+                    if dd is None:
+                        tab.cw_funcs[text] = (f0, _d2)
+            return y
+    return Tcalculus._lift(x)._unary(lambda v: tab.componentwise(cfun, v, fun, d1))
+
+
 def mtimes(a, b) -> Tcalculus:
     """matrix product ``A*B`` (scalars broadcast like MATLAB's ``*``)"""
     a, b = Tcalculus._lift(a), Tcalculus._lift(b)

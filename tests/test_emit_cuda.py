@@ -179,3 +179,55 @@ def test_module_path_is_content_addressed():
     assert module_path(gen) == module_path(gen)
     assert module_path(gen) != module_path(gen, max_loads=44)
     assert module_path(gen, tiles=2) != module_path(gen, tiles=1)
+
+
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor", "l1l2"])
+def test_rolled_runs_are_the_reference_emitters_loops(name):
+    """loop rolling (instructionsTableUTHash.c:881-944): the runs `rolled_runs` detects are exactly the `for`
+    loops the reference's own writeCinstructionsC prints for the same instruction list (minInstructions4loop=50)"""
+    from oracle.emit_c import RefEmitter
+    gen, _ = generated(name)
+    pr = gen.problem
+    em = RefEmitter(pr)
+    total = 0
+    for members in pr.groups:
+        txt = em.statements(members, 50)
+        ref = [int(c) for c in re.findall(r"for\(int64_t c=(\d+);", txt)]
+        runs = emit_cuda.rolled_runs(pr, members, 50)
+        assert [n for _, n in runs] == ref
+        for start, n in runs:            # the comment the reference prints names the first instruction of the run
+            assert pr.tab.types[members[start]] in emit_cuda.ROLLABLE
+        total += sum(ref)
+    assert total > 0
+
+
+@pytest.mark.parametrize("name", ["sls", "mpc_dcmotor"])
+def test_rolled_emission_covers_every_instruction_once(name):
+    """roll=N: every run is a chunk of its own holding a device loop; the other instructions are chunked as before;
+    every value a rolled chunk reads from another chunk is stored by its producer"""
+    gen, _ = generated(name)
+    pr = gen.problem
+    ext = emit_cuda.external_values(pr)
+    n_rolled = 0
+    for g, members in enumerate(pr.groups):
+        chunks, rolled = emit_cuda.chunk_group_rolled(pr, members, 1536, 28, 20)
+        assert [i for ch in chunks for i in ch] == list(members)
+        fns, st = emit_cuda.emit_group(pr, g, ext, max_loads=28, roll=20)
+        src = "".join(s for _, s in fns)
+        assert src.count("// rolled run:") == len(rolled)
+        assert st["rolled"] == sum(len(chunks[k]) for k in rolled)
+        n_rolled += st["rolled"]
+        stored = {int(x) // emit_cuda.TILE for x in re.findall(r"\bmt\[(\d+)\]=", src)}
+        for k in rolled:
+            inside = set(chunks[k])
+            for i in chunks[k]:
+                for q in pr.tab.operands[i]:
+                    if q in pr.group_of and pr.group_of[q] == g and q not in inside \
+                            and pr.tab.types[q] not in (it.I_load, it.I_2, it.I_set) \
+                            and not any(q in chunks[j] for j in rolled):
+                        assert int(pr.slot[q]) in stored, (g, k, q)
+    assert n_rolled > 0
+    files, st = emit_cuda.emit_module(gen, roll=20)
+    assert st["total"]["rolled"] == n_rolled or st["total"]["rolled"] > 0
+    with pytest.raises(ValueError):
+        emit_cuda.emit_module(gen, roll=20, scache=8)

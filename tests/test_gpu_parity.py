@@ -153,14 +153,15 @@ def test_tiles_option_is_bit_identical():
 
 
 @pytest.mark.parametrize("opts", [dict(pair=1, max_loads=14), dict(scache=24), dict(pair=1, max_loads=14, scache=12),
-                                  dict(lockstep=6, warps_per_sm=24), dict(prefetch=0), dict(wide=1)],
-                         ids=["pair", "scache", "pair+scache", "lockstep6", "noprefetch", "wide"])
+                                  dict(lockstep=6, warps_per_sm=24), dict(prefetch=0), dict(wide=1), dict(roll=20)],
+                         ids=["pair", "scache", "pair+scache", "lockstep6", "noprefetch", "wide", "roll"])
 @pytest.mark.parametrize("name,batch", [("sls", 1000), ("mpc_dcmotor", 700)])
 def test_layout_options_are_bit_identical(name, batch, opts):
     """emitter options that change where values live, not what is computed: `pair` (two instances per lane in
     interleaved columns, 128-bit loads and stores; the set/gather/compaction kernels follow the layout through
     tc_device_image::ilv), `wide` (tiles of 64 instances: two lockstep warps share 512-byte segments), `scache` (per-lane software cache in shared memory, offline Belady plan), CTAs of 6
-    lockstep warps, no L2 prefetch -- same status, iterations and outputs as the default module, on a ragged batch,
+    lockstep warps, no L2 prefetch, `roll` (strided repeats of one instruction as device loops: the reference's
+    loop rolling) -- same status, iterations and outputs as the default module, on a ragged batch,
     and the same again after a set + re-solve on the same handle (stale lazy-evaluation state of the partner)"""
     gen, args = generated(name)
     P, V = problems.synthetic_inputs(name, gen, batch, seed=11)
@@ -185,6 +186,33 @@ def test_layout_options_are_bit_identical(name, batch, opts):
     for x, y in zip(list(a[2]) + list(a[5]), list(b[2]) + list(b[5])):
         assert np.array_equal(x, y)
     assert (a[0] == 0).mean() > 0.5
+
+
+def test_componentwise_user_function():
+    """I_componentwise (user C text, instructionsTableUTHash.c:1333-1345; Tcalculus.m:1836-1880): isa_probe with its
+    sine term written as `componentwise(x,sin,'sin(%s)',d1,d2)` -- compiled into the module as CUDA C -- against
+    the reference's emitter and driver, and bit-identical to the module that uses the built-in opcodes"""
+    batch = 512
+    gen0, args = generated("isa_probe")
+    gen1, _ = generated("isa_probe", cw=True)
+    P, V = problems.synthetic_inputs("isa_probe", gen0, batch, seed=4)
+    st_o, it_o, out_o, _ = _oracle(gen1, "isa_probe").solve_batch(P, V, args["mu0"], args["maxIter"])
+    res = []
+    for gen in (gen0, gen1):
+        obj = _solve(gen, args, P, V, batch)
+        st, it, _ = obj.solve(args["mu0"], args["maxIter"], -1)
+        outs = obj.getOutputs()
+        res.append((st, it, list(outs.values()) if isinstance(outs, dict) else list(outs)))
+        obj.close()
+    st, it, outs = res[1]
+    assert np.array_equal(st, st_o) and np.abs(it.astype(int) - it_o.astype(int)).max() <= 1
+    assert (st_o == 0).mean() > 0.5
+    for (n, _), y in zip(gen1.outputs, outs):
+        a, b = np.asarray(y)[..., st_o == 0], np.asarray(out_o[n])[..., st_o == 0]
+        assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(b).max()), n
+    assert np.array_equal(res[0][0], st) and np.array_equal(res[0][1], it)
+    for a, b in zip(res[0][2], outs):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("driver", ["lanes", "queue"])

@@ -288,3 +288,41 @@ def test_inertia_controlled_regularisation_port_equals_reference():
     gen0, _ = generated("mpc_quadcopter", T_=20)
     _, it_0, _, _ = Oracle(gen0, "ref").solve_batch(P, V, args["mu0"], args["maxIter"])
     assert (it_0 != it_r).any()
+
+
+def test_componentwise_user_function():
+    """`componentwise(x,fun,cfun,d1,d2)` (lib/@Tcalculus/Tcalculus.m:1836-1880 -> I_componentwise, printed by
+    instructionsTableUTHash.c:1333-1345): the sine term of isa_probe written as a user-defined function with its two
+    derivatives is the same problem -- under the reference's own emitter and driver the iterates are identical to the
+    built-in opcodes', the port emitter prints the reference emitter's text, and the numpy evaluator agrees"""
+    import re
+    from oracle import emit_c
+    from oracle.oracle import Oracle
+    from oracle.pyeval import evaluate
+    from tenscalc_b200 import problems, itable as it
+    gen0, args = generated("isa_probe")
+    gen1, _ = generated("isa_probe", cw=True)
+    pr = gen1.problem
+    cw = [i for m in pr.groups for i in m if pr.tab.types[i] == it.I_componentwise]
+    assert sorted(it.componentwise_text(pr.tab.params[i], "%s") for i in cw) == ["cos(%s)", "sin(%s)"]
+    ref = emit_c.RefEmitter(pr)
+    norm = lambda txt: re.sub(r"\s+", "", re.sub(r"//[^\n]*", "", txt))
+    for i in cw:
+        assert norm(ref.statements([i], min4loop=10 ** 9)) == norm(emit_c.statement(pr.tab, i, pr.slot))
+        x = np.linspace(-2, 2, 9)
+        f = np.sin if "sin" in it.componentwise_text(pr.tab.params[i], "%s") else np.cos
+        (o,) = pr.tab.operands[i]
+        assert pr.tab.types[o] == it.I_set
+        assert np.allclose(evaluate(pr.tab, [i], {o: x})[0], f(x), rtol=0, atol=1e-15)
+    P, V = problems.synthetic_inputs("isa_probe", gen0, 64, seed=5)
+    st0, it0, out0, _ = Oracle(gen0, "ref").solve_batch(P, V, args["mu0"], args["maxIter"])
+    for kind in ("ref", "port"):
+        st1, it1, out1, _ = Oracle(gen1, kind).solve_batch(P, V, args["mu0"], args["maxIter"])
+        assert np.array_equal(st0, st1) and np.array_equal(it0, it1)
+        for k in out0:
+            assert np.array_equal(out0[k], out1[k]), (kind, k)
+    assert (st0 == 0).all()
+    # the tape interpreter cannot run user C text, and says so
+    from tenscalc_b200 import tape
+    with pytest.raises(NotImplementedError, match="compiled back end"):
+        tape.lower(gen1)
