@@ -112,7 +112,9 @@ __device__ __forceinline__ double tc_unary(int op, double x) {
     case I_relu: return (x > 0) ? x : 0.0;
     case I_heaviside: return (x > 0) ? 1.0 : 0.0;
     }
-    return x;
+    // not an opcode the interpreter knows (I_componentwise: user C text, compiled modules only): NaN, so that
+    // a handle that runs such a tape without its module fails loudly (status 4) instead of computing something else
+    return __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // every cell kind except OP_MADD, out of line so that the hot path stays small

@@ -150,7 +150,7 @@ class BatchedSolver:
         self.gen = gen
         self.batch = int(batch)
         self.device = int(device if device is not None else os.environ.get("LOCAL_RANK", 0))
-        self._image = tape.serialize(gen)
+        self._image = tape.serialize(gen, compiled=(backend == "compiled"))
         h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(self._image, len(self._image))
         _check(lib.tc_create(ctypes.byref(h), buf, len(self._image), self.batch, self.device))

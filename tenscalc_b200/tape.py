@@ -148,7 +148,7 @@ def persistent_state(pr: CompiledProblem):
 SELF = ("self", 0)           # operand token: the ring entry of the instruction being lowered
 
 
-def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
+def instruction_cells(t: int, p, opw: List[int], compiled: bool = False) -> List[List[int]]:
     """Cells [op, flags, A, B] of one instruction; ``opw`` are operand tokens in the reference's
     operand order (``None`` marks an unused operand).  The arithmetic order is that of the emitted C statement
     (instructionsTableUTHash.c:950-1539)."""
@@ -242,15 +242,21 @@ def instruction_cells(t: int, p, opw: List[int]) -> List[List[int]]:
     elif t in it.UNARY_TYPES:
         c.append([OP_UNARY + t, 0, opw[0], N])
     elif t == it.I_componentwise:
-        raise NotImplementedError("I_componentwise is user C text: it needs the compiled back end (backend='compiled'), "
-                                  "the tape interpreter cannot run it")
+        # user C text: only the compiled module can run it.  An image made for the compiled back end carries a
+        # placeholder cell (the interpreter evaluates unknown unary opcodes to NaN: loud, never silently wrong)
+        if not compiled:
+            raise NotImplementedError("I_componentwise is user C text: it needs the compiled back end "
+                                      "(backend='compiled'), the tape interpreter cannot run it")
+        c.append([OP_UNARY + t, 0, opw[0], N])
     else:
         raise NotImplementedError(it.OPNAMES.get(t, str(t)))
     c[-1][1] |= F_END
     return c
 
 
-def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[str, np.ndarray]:
+def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE, compiled: bool = False) -> Dict[str, np.ndarray]:
+    """``compiled``: the image is for a handle that runs the problem's compiled module -- instructions only the
+    module can evaluate (``I_componentwise``) are accepted and lowered to placeholder cells"""
     pr: CompiledProblem = gen.problem
     tab, slot = pr.tab, pr.slot
     if pr.n_slots * TILE_BYTES >= 1 << 32:
@@ -336,7 +342,7 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
                     else:
                         opw.append(("slot", int(slot[o])))
                         stats["slot_reads"] += 1
-            cs = instruction_cells(t, p, opw)
+            cs = instruction_cells(t, p, opw, compiled)
             store = i in external or far.get(i, 0) >= ring
             stats["stores" if store else "ring_only"] += 1
             self_ring[0] = n % ring
@@ -404,8 +410,8 @@ def lower(gen: GeneratedSolver, ring: int = RING, bundle: int = BUNDLE) -> Dict[
                 stats=stats)
 
 
-def serialize(gen: GeneratedSolver) -> bytes:
-    L = lower(gen)
+def serialize(gen: GeneratedSolver, compiled: bool = False) -> bytes:
+    L = lower(gen, compiled=compiled)
     d = gen.defines
     ih = np.zeros(64, dtype=np.int64)
     ih[0] = MAGIC

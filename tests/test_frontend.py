@@ -64,6 +64,51 @@ def test_gradient_and_hessian_against_finite_differences():
     assert np.abs(Hv - Hv.T).max() <= 1e3 * EPS * np.abs(Hv).max()
 
 
+def test_componentwise_user_function_derivatives():
+    """componentwise(x,fun,cfun,derivative1,derivative2) (lib/@Tcalculus/Tcalculus.m:1836-1880): a user-defined
+    tanh with its derivatives written in terms of itself -- gradient and Hessian by the chain rule against finite
+    differences; constants fold through the Python form, structural zeros through fun(0); without a derivative the
+    differentiator refuses"""
+    import math
+    T.clear()
+    tab = T.table()
+
+    def tanh_(z):
+        return T.componentwise(z, math.tanh, "tanh(%s)", lambda w: 1.0 - T.sqr(tanh_(w)))
+
+    x = T.Tvariable("x", 3)
+    p = T.Tvariable("p", 3)
+    f = T.tsum(tanh_(x * p) * x, 0) + T.tsum(T.sqr(tanh_(x)), 0)
+    u = x.flat()
+    H, g = hessian(tab, f.e[()], u)
+    assert any(tab.types[i] == it.I_componentwise for i in tab.ancestors([f.e[()]]))
+    rng = np.random.default_rng(3)
+    x0, p0 = rng.normal(size=3), rng.uniform(.5, 1.5, size=3)
+    vals = lambda xv: {**_vals(x, xv), **_vals(p, p0)}
+    fval = lambda xv: evaluate(tab, [f.e[()]], vals(xv))[0][0]
+    gval = lambda xv: np.array([evaluate(tab, [gi], vals(xv))[0][0] for gi in g])
+    h = 1e-6
+    gn = np.array([(fval(x0 + h * e) - fval(x0 - h * e)) / (2 * h) for e in np.eye(3)])
+    assert np.abs(gval(x0) - gn).max() <= 1e-7 * max(1, np.abs(gn).max())
+    Hv = np.zeros((3, 3))
+    for i in range(3):
+        for j, e in H[i].items():
+            Hv[i, j] = evaluate(tab, [e], vals(x0))[0][0]
+    Hn = np.array([(gval(x0 + h * e) - gval(x0 - h * e)) / (2 * h) for e in np.eye(3)])
+    assert np.abs(Hv - Hn).max() <= 1e-6 * max(1, np.abs(Hn).max())
+    # constants and structural zeros
+    c = T.componentwise(T.Tconstant([0.5, 0.0]), math.cos, "cos(%s)")
+    assert [tab.const_value(i) for i in c.flat()] == [math.cos(0.5), 1.0]
+    assert T.componentwise(T.Tconstant([0.0]), math.tanh, "tanh(%s)").flat() == [None]
+    # the C text is what the emitters print, operand at every %s (instructionsTableUTHash.c:1333-1345)
+    y = T.componentwise(x, lambda v: v * abs(v), "%s*fabs(%s)")
+    assert it.componentwise_text(tab.params[y.flat()[0]], "m[7]") == "m[7]*fabs(m[7])"
+    with pytest.raises(NotImplementedError, match="no derivative"):
+        gradient(tab, T.tsum(y, 0).e[()], u)
+    with pytest.raises(ValueError):
+        T.componentwise(x, math.sin, "sin(x)")
+
+
 @pytest.mark.parametrize("n,density,seed", [(5, .75, 0), (6, .75, 1), (12, .3, 2), (20, .2, 3)])
 def test_ldl_identity_and_solve(n, density, seed):
     """testFactorizations.m:46-91 (L*D*L'=A on random 75%-dense matrices) and testLDL.m

@@ -326,3 +326,7 @@ def test_componentwise_user_function():
     from tenscalc_b200 import tape
     with pytest.raises(NotImplementedError, match="compiled back end"):
         tape.lower(gen1)
+    # ... while the image of a handle that runs the compiled module carries placeholder cells for them
+    L = tape.lower(gen1, compiled=True)
+    assert (L["tape"][:, 0] & 0x7f == tape.OP_UNARY + it.I_componentwise).sum() == len(cw)
+    assert len(tape.serialize(gen1, compiled=True)) > 0
