@@ -75,7 +75,13 @@ int tc_set_device(tc_solver *s, int set_index, const double *d_values, int64_t b
  * Inputs by pointer as in the reference; `status` and
  * `iter` are int32[batch]; `time` receives the device time of the whole batch in seconds.
  * tc_solve copies status/iter to host memory; tc_solve_device leaves them on the device and
- * does not synchronise the host (`time` may be NULL). */
+ * does not synchronise the host (`time` may be NULL).
+ * `saveIter` (lib/ipmPD_CSsolver.c:136) only matters for a class generated with allowSave
+ * (lib/cmex2optimizeCS.m:267,327): where the reference's driver calls saveWW__ -- iteration == saveIter, a
+ * successful exit when saveIter == 0, a failed factorisation (:330-332,561-566,671-676,699-703,877-882) --
+ * every instance keeps the values of its KKT matrix, and getOutputs returns them as one more, last, output
+ * (structural non-zeros in column-major order of their subscripts).  Other classes ignore it, as the
+ * reference does. */
 int tc_solve(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
              const double *addEye2Hessian, int32_t *status, int32_t *iter, double *time);
 int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,

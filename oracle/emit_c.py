@@ -222,8 +222,17 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
         w(f"EXPORT void {fname}(const double *input) {{\n  SCRATCHBOOK_TYPE *m=scratchbook;\n")
         w("".join(f"  m[{slot[d]}]=*(input++);\n" for d in s.dest))
         w(_invalidate(s.children) + "}\n")
+    if int(pr.defines.get("allowSave", 0)):
+        # allowSave: the reference's driver calls saveWW__(saveNamePrefix "_WW.values") (ipmPD_CSsolver.c:51,330-332,
+        # 561-566,671-676,699-703,877-882).  The oracle's saveWW__ is the copy of the KKT values into the save
+        # variables that getOutputs returns (optimize.py), the file name is ignored (the driver still prints its
+        # "Saving ..." line per event).  Only the reference's own driver carries the save hooks.
+        if driver != "ref":
+            raise NotImplementedError("allowSave: use the reference's driver as oracle (kind='ref')")
+        w('#define saveNamePrefix "oracle"\n')
     for c in pr.copies.values():
-        w(f"EXPORT void {c.name}(void) {{\n  SCRATCHBOOK_TYPE *m=scratchbook;\n" + _run_groups(c.parents))
+        sig = "char *filename" if c.name == "saveWW__" else "void"
+        w(f"EXPORT void {c.name}({sig}) {{\n  SCRATCHBOOK_TYPE *m=scratchbook;\n" + _run_groups(c.parents))
         w("".join(f"  m[{slot[d]}]=m[{slot[s]}];\n" for d, s in zip(c.dest, c.src) if d != s))
         w(_invalidate(c.children) + "}\n")
     for g in pr.gets.values():

@@ -397,7 +397,7 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     D.useInertia = (int32_t)ih[24]; D.skipAffine = (int32_t)ih[25]; D.delta = (int32_t)ih[26];
     D.driver = (int32_t)ih[27];
     if (D.driver < 0 || D.driver > 2) { tc_destroy(s); return TC_EFORMAT; }
-    D.mpUdesired = (int32_t)ih[28]; D.mnDdesired = (int32_t)ih[29]; D.pad_ = 0;
+    D.mpUdesired = (int32_t)ih[28]; D.mnDdesired = (int32_t)ih[29]; D.allowSave = (int32_t)ih[30];
     D.addEye2HessianDtolerance = dh[8];
     if (D.driver == 2 && (n_funcs <= FN_getHessUinertia || (D.setAddEye2Hessian && D.adjustAddEye2Hessian &&
                                                             !funcs[FN_getHessUinertia].io_cnt))) {
@@ -587,10 +587,12 @@ int tc_set_phased(tc_solver *s, int on) {
 int tc_solve_device(tc_solver *s, const double *mu0, const int32_t *maxIter, const int32_t *saveIter,
                     const double *addEye2Hessian, int32_t *d_status, int32_t *d_iter) {
     if (!s || !mu0 || !maxIter || !addEye2Hessian || !d_status || !d_iter) return TC_EINVAL;
-    // saveIter: the reference dumps the KKT matrix values at that iteration when the solver was GENERATED with
-    // allowSave (cmex2optimizeCS.m:326, ipmPD_CSsolver.c:562-564,672-674); the generators here always emit
-    // allowSave=0, for which the reference ignores the argument too
-    (void)saveIter;
+    // saveIter: when the solver was GENERATED with allowSave (cmex2optimizeCS.m:327) the reference dumps the KKT
+    // matrix values of that iteration to a file (ipmPD_CSsolver.c:562-564,672-674); here every instance keeps them
+    // in its save variables and getOutputs returns them as the last output (tc_driver.cuh).  Without allowSave the
+    // argument is ignored, as in the reference.
+    if (s->img.def.allowSave && !saveIter) return TC_EINVAL;
+    s->img.save_iter = (s->img.def.allowSave && saveIter) ? *saveIter : -1;
     if (!s->module && s->img.n_consts > TC_MAXCONST) return TC_EFORMAT;   // interpreter: constant pool lives in shared memory
     TC_CUDA(cudaSetDevice(s->device));
     TC_CUDA(cudaEventRecord(s->ev0, s->stream));

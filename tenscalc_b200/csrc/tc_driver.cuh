@@ -83,6 +83,17 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
     // retries (:238-301), other barrier thresholds (:411-440), 2048 bit from either tolerance (:503-507).
     const bool mm = D.driver == 2;
     tc_bT run, updU, updEq, updD, pr, pr2;
+    // allowSave (cmex2optimizeCS.m:327): saveWW__ -- in the reference a dump of the KKT matrix values to a file -- is a
+    // copy of those values into the instance's save variables, which getOutputs returns as its last output.  The
+    // events are the reference's: a failed factorisation (status 4, :330-332,700-702), iter == saveIter
+    // (:561-566,671-676) and saveIter == 0 at a successful exit (:877-882).  `sv` marks the lanes of an event.
+    tc_bT sv;
+    TC_FORT sv[t] = false;
+#define TC_SAVE_WW()                                                                                  \
+    if (D.allowSave && !eq && !mm) {                                                                  \
+        if (tc_any_tile(sv)) tc_copy(c, P, FN_saveWW, sv);                                            \
+        TC_FORT sv[t] = false;                                                                        \
+    }
     tc_iT status, iter, ls;
     tc_dT aeU, aeEq, aeD, mu, muMin, gapTol, alphaMax_, alphaPrimal, alphaDualEq, alphaDualIneq;
     tc_dT norminf_grad, norminf_eq, gap, ineq, ineq1, dual, v0, v1, v2, mp, mn;
@@ -141,8 +152,9 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         tc_value(c, P, FN_getNorminf_Grad, 0, run, v0);
         TC_FORT {
             if (run[t]) norminf_grad[t] = v0[t];
-            if (run[t] && isnan(norminf_grad[t])) { status[t] = 4; run[t] = false; }
+            if (run[t] && isnan(norminf_grad[t])) { status[t] = 4; run[t] = false; sv[t] = true; }
         }
+        TC_SAVE_WW();                                                       // :329-332
         if (hasG) {
             tc_get(c, P, FN_getNorminf_G, run);
             tc_value(c, P, FN_getNorminf_G, 0, run, v0);
@@ -307,6 +319,8 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         if (!hasF) {                                                        // :550-569
             tc_set_scalar(c, P, FN_setAlphaPrimal, alphaMax_, run);
             if (hasG) tc_set_scalar(c, P, FN_setAlphaDualEq, alphaMax_, run);
+            TC_FORT sv[t] = run[t] && iter[t] == P.save_iter;               // :561-566
+            TC_SAVE_WW();
             tc_copy(c, P, FN_updatePrimalDual, run);
             continue;
         }
@@ -379,6 +393,8 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         }
 
         // ---- combined search direction (:679-772) ----
+        TC_FORT sv[t] = run[t] && iter[t] == P.save_iter;                   // :671-676
+        TC_SAVE_WW();
         tc_get(c, P, FN_getMaxAlphas_s, run);
         tc_value(c, P, FN_getMaxAlphas_s, 0, run, v0);
         tc_value(c, P, FN_getMaxAlphas_s, 1, run, v1);
@@ -413,7 +429,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
                 if (ev[t]) switch (ls[t]) {
                 case LS_TRYMAX:                                             // :693-714
                     ineq[t] = f;
-                    if (isnan(ineq[t])) { status[t] = 4; run[t] = false; ls[t] = LS_DONE; }
+                    if (isnan(ineq[t])) { status[t] = 4; run[t] = false; ls[t] = LS_DONE; sv[t] = true; }
                     else if (ineq[t] > 0) { alphaPrimal[t] *= TC_stepback; ls[t] = LS_RECHECK; }
                     else { alphaPrimal[t] = D.alphaMin / TC_stepback; ls[t] = LS_TRYMIN; }
                     break;
@@ -451,6 +467,7 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
                     break;
                 }
             }
+            TC_SAVE_WW();                                                   // :699-703
         }
 
         TC_FORT if (run[t]) {                                               // :758-767
@@ -539,6 +556,9 @@ __device__ __forceinline__ void tc_ipm_solve(tc_lane &c, const tc_device_image &
         tc_set_scalar(c, P, FN_setMu, mu, pr);
     }
 
+    TC_FORT sv[t] = entered[t] && !run[t] && status[t] == 0 && P.save_iter == 0;   // :877-882
+    TC_SAVE_WW();
+#undef TC_SAVE_WW
     // ---- diagnostic bits when maxIter was reached (:885-920) ----
     tc_bT diag;
     TC_FORT diag[t] = entered[t] && !run[t] && status[t] == 8;

@@ -46,6 +46,7 @@ enum tc_fn {
     FN_setAlphaDualIneq, FN_updatePrimalDual, FN_getJ, FN_getOutputs,
     FN_getMaxAlphas_a, FN_getMinF_a, FN_getRho,      // affine-scaling (Mehrotra) step, skipAffine=0 (ipmPD_CS.m:313-315,422-425)
     FN_setAddEye2HessianD, FN_getHessDinertia, FN_getHessUinertia,   // min-max driver (ipmPDminmax_CS.m:181-192,266-272)
+    FN_saveWW,               // allowSave: saveWW__ (ipmPD_CSsolver.c:51) as a copy of the KKT values into save variables
     FN_USER0
 };
 
@@ -72,7 +73,8 @@ struct tc_defines {         // the #define table of lib/cmex2optimizeCS.m:303-33
         useInertia, skipAffine, delta;
     int32_t driver;         // 0: ipmPD_CSsolver (lib/ipmPD_CSsolver.c), 1: ipmPDeq_CSsolver (lib/ipmPDeq_CSsolver.c),
                             // 2: ipmPDminmax_CSsolver (lib/ipmPDminmax_CSsolver.m)
-    int32_t mpUdesired, mnDdesired, pad_;   // min-max: wanted inertia (ipmPDminmax_CSsolver.m:68-69)
+    int32_t mpUdesired, mnDdesired;         // min-max: wanted inertia (ipmPDminmax_CSsolver.m:68-69)
+    int32_t allowSave;                      // the solver was generated with allowSave (cmex2optimizeCS.m:327)
     double addEye2HessianDtolerance;
     double gradTolerance, addEye2HessianUtolerance, equalTolerance, desiredDualityGap, alphaMin,
         alphaMax, muFactorAggressive, muFactorConservative;
@@ -117,6 +119,10 @@ struct tc_device_image {    // device pointers, passed by value to the kernels
     // 1: tiles of 64 instances, m[tile][slot][64] (emitter option wide): the two warps of a lockstep CTA that sit on
     // neighbouring 32-instance blocks touch the two 256-byte halves of one 512-byte segment at about the same time
     int32_t wide;
+    // saveIter of this solve (ipmPD_CSsolver.c:136): with allowSave, the Newton iteration whose KKT values are kept
+    // (0: the values at a successful exit; status 4 keeps them too, :330-332,700-702,877-882)
+    int32_t save_iter;
+    int32_t pad_;
 };
 #define TC_PS_ND 12
 #define TC_PS_NI 2

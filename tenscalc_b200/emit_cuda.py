@@ -548,6 +548,8 @@ def emit_module(gen, max_refs: int = 1536, max_loads: int = 96, part_bytes: int 
             total[k] += st[k]
     copy_calls: Dict[int, List[str]] = {}
     from .tape import driver_of, fn_items
+    if int((pr.defines or {}).get("allowSave", 0)) and driver != "warp":
+        raise ValueError("allowSave: the save events are implemented by the warp driver only")
     if driver_of(pr) != "ipmPD_CSsolver" and driver != "warp":
         raise ValueError("the lane-decoupled and work-queue drivers implement ipmPD_CSsolver only")
     for name, fid in fn_items(pr):

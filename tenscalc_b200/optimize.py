@@ -49,7 +49,7 @@ def solver_defines(nU: int, nG: int, nF: int, *, gradTolerance: float = 1e-4, eq
                    skipAffine: bool = True, delta: int = 3, scaleInequalities: bool = True, scaleCost: float = 0.0,
                    scaleEqualities: bool = False, addEye2Hessian: bool = True, adjustAddEye2Hessian: bool = True,
                    useInertia: bool = False, addEye2HessianUtolerance: float = 1e-6, solverVerboseLevel: int = 1,
-                   smallerNewtonMatrix: bool = False, **ignored) -> Dict[str, object]:
+                   smallerNewtonMatrix: bool = False, allowSave: bool = False, **ignored) -> Dict[str, object]:
     """the #define table cmex2optimizeCS hands to the C driver (lib/cmex2optimizeCS.m:303-331; defaults
     lib/private/parameters4all.m, parameters4optimize.m)"""
     return dict(
@@ -62,8 +62,8 @@ def solver_defines(nU: int, nG: int, nF: int, *, gradTolerance: float = 1e-4, eq
         setAddEye2Hessian=int(bool(addEye2Hessian)), adjustAddEye2Hessian=int(bool(adjustAddEye2Hessian)),
         useInertia=int(bool(useInertia)), muFactorAggressive=float(muFactorAggressive),
         muFactorConservative=float(muFactorConservative), delta=int(delta), skipAffine=int(bool(skipAffine)),
-        smallerNewtonMatrix=int(bool(smallerNewtonMatrix)), useLDL=1, useUmfpack=0, allowSave=0, debugConvergence=0,
-        profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
+        smallerNewtonMatrix=int(bool(smallerNewtonMatrix)), useLDL=1, useUmfpack=0, allowSave=int(bool(allowSave)),
+        debugConvergence=0, profiling=0, verboseLevel=int(min(solverVerboseLevel, 1)))
 
 
 def _name_of(v: Tcalculus) -> str:
@@ -88,7 +88,7 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
                     smallerNewtonMatrix: bool = False, useUmfpack: bool = False,
                     sensitivityVariables: Sequence[Tcalculus] = (),
                     solverVerboseLevel: int = 1, ordering=None, algorithm: str = "ipmPD_CStimesLambda",
-                    **ignored) -> GeneratedSolver:
+                    allowSave: bool = False, **ignored) -> GeneratedSolver:
     # the reference's C generator hard-wires algorithm 3 and rejects the options below
     # (cmex2optimizeCS.m:83-93, ipmPD_CStimesLambda.m:31-48)
     # ``algorithm`` selects the symbolic builder: "ipmPD_CStimesLambda" is what the shipped generator always
@@ -168,6 +168,22 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
         shapes.append(e.shape)
         names.append(nm)
         out_info.append((nm, e.shape))
+    # ---- allowSave (cmex2optimizeCS.m:267,327; ipmPD_CStimesLambda.m:288-290 declareSave(code,WW,'saveWW__',...)) ----
+    # The reference's saveWW__ writes the values of WW's structural non-zeros to `<class>_WW.values` (their
+    # subscripts to `<class>_WW.subscripts` at generation time).  A batch has no file per instance: saveWW__ is a
+    # copy of those values into save variables that getOutputs returns as one more, last, output `WW_values__`
+    # (subscripts: info["WW_subscripts"], column-major order like the reference's tensors).
+    ww_subs = None
+    if allowSave:
+        WW = info["WW"]
+        entries = sorted((c, r, x) for r, row in enumerate(WW) for c, x in row.items() if x is not None)
+        ww_subs = np.array([(r, c) for c, r, _ in entries], dtype=np.int64).reshape(-1, 2)
+        store = [tab.new_set(f"WW_saved__[{k}]") for k in range(len(entries))]
+        code.declare_copy("saveWW__", store, [x for _, _, x in entries])
+        srcs.append(store)
+        shapes.append((len(store),))
+        names.append("WW_values__")
+        out_info.append(("WW_values__", (len(store),)))
     code.declare_get("getOutputs", srcs, shapes, names)
 
     defines = solver_defines(len(u), len(G), len(F), gradTolerance=gradTolerance, equalTolerance=equalTolerance,
@@ -177,7 +193,8 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
                              scaleInequalities=scaleInequalities, scaleCost=scaleCost, scaleEqualities=scaleEqualities,
                              addEye2Hessian=addEye2Hessian, adjustAddEye2Hessian=adjustAddEye2Hessian,
                              useInertia=useInertia, addEye2HessianUtolerance=addEye2HessianUtolerance,
-                             solverVerboseLevel=solverVerboseLevel, smallerNewtonMatrix=smallerNewtonMatrix)
+                             solverVerboseLevel=solverVerboseLevel, smallerNewtonMatrix=smallerNewtonMatrix,
+                             allowSave=allowSave)
     problem = code.compile(defines)
     fac = info["factor"]
     from .ordering import DEFAULT as default_ordering
@@ -187,6 +204,8 @@ def cmex2optimizeCS(*, classname: str, objective: Tcalculus,
                     nnzL=fac.nnz(), kkt=fac.n, n_instructions=sum(len(g) for g in problem.groups),
                     n_groups=len(problem.groups), n_slots=problem.n_slots,
                     dense_block=ldl_dense_block(fac))
+    if ww_subs is not None:
+        gen_info["WW_subscripts"] = ww_subs
     return GeneratedSolver(classname, problem, par_info, var_info, out_info, is_struct, defines, gen_info)
 
 

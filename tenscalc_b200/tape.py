@@ -84,7 +84,8 @@ FN = {name: k for k, name in enumerate([
     "getHessInertia__", "getMaxAlphas_s__", "setAlphaPrimal__", "getMinF_s__", "setAlphaDualEq__",
     "setAlphaDualIneq__", "updatePrimalDual__", "getJ__", "getOutputs",
     "getMaxAlphas_a__", "getMinF_a__", "getRho__",
-    "setAddEye2HessianD__", "getHessDinertia__", "getHessUinertia__"])}
+    "setAddEye2HessianD__", "getHessDinertia__", "getHessUinertia__",
+    "saveWW__"])}               # allowSave (ipmPD_CSsolver.c:51): copy of the KKT values into their save variables
 FN_USER0 = len(FN)
 # the equilibrium driver (lib/ipmPDeq_CSsolver.c:28-52) calls three of the slots by other names
 EQ_NAMES = {"setAddEye2HessianU__": "setAddEye2Hessian1__", "setAddEye2HessianEq__": "setAddEye2Hessian2__",
@@ -427,6 +428,7 @@ def serialize(gen: GeneratedSolver, compiled: bool = False) -> bytes:
         ih[16] = d["nZ"]          # the device driver only tests nG > 0 / nF > 0 and divides by nF
     if ih[27] == 2:
         ih[28:30] = (d["mpUdesired"], d["mnDdesired"])
+    ih[30] = int(d.get("allowSave", 0))
     dh = np.zeros(16, dtype=np.float64)
     dh[0:8] = (d["gradTolerance"], d["addEye2HessianUtolerance"], d["equalTolerance"], d["desiredDualityGap"],
                d["alphaMin"], d["alphaMax"], d["muFactorAggressive"], d["muFactorConservative"])

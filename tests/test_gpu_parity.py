@@ -188,6 +188,31 @@ def test_layout_options_are_bit_identical(name, batch, opts):
     assert (a[0] == 0).mean() > 0.5
 
 
+@pytest.mark.parametrize("backend", ["compiled", "tape"])
+def test_allow_save_keeps_the_kkt_values(backend):
+    """allowSave / saveIter (ipmPD_CSsolver.c:136,330-332,561-566,671-676,877-882): a solver generated with
+    allowSave keeps, per instance, the KKT matrix values of iteration saveIter (saveIter = 0: at the successful
+    exit) and returns them as the last output -- identical to what the reference's driver hands to saveWW__, with
+    the solve itself unchanged; phased (compiled) and single-launch (tape) execution"""
+    batch = 300
+    gen0, args = generated("mpc_dcmotor")
+    gen, _ = generated("mpc_dcmotor", allowSave=True)
+    P, V = problems.synthetic_inputs("mpc_dcmotor", gen0, batch, seed=6)
+    for save_iter in (3, 0):
+        st_o, it_o, out_o, _ = _oracle(gen, "mpc_dcmotor").solve_batch(P, V, args["mu0"], args["maxIter"], saveIter=save_iter)
+        assert (st_o == 0).all() and it_o.min() > 3
+        obj = _solve(gen, args, P, V, batch, backend=backend)
+        st, it, _ = obj.solve(args["mu0"], args["maxIter"], save_iter)
+        outs = obj.getOutputs()
+        outs = outs if isinstance(outs, dict) else {n: o for (n, _), o in zip(gen.outputs, outs)}
+        obj.close()
+        assert np.array_equal(st, st_o) and np.array_equal(it, it_o)
+        for k in out_o:
+            a, b = np.asarray(outs[k]), np.asarray(out_o[k])
+            assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(b).max()), (save_iter, k)
+        assert np.abs(outs["WW_values__"]).sum() > 0
+
+
 def test_componentwise_user_function():
     """I_componentwise (user C text, instructionsTableUTHash.c:1333-1345; Tcalculus.m:1836-1880): isa_probe with its
     sine term written as `componentwise(x,sin,'sin(%s)',d1,d2)` -- compiled into the module as CUDA C -- against

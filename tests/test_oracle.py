@@ -330,3 +330,40 @@ def test_componentwise_user_function():
     L = tape.lower(gen1, compiled=True)
     assert (L["tape"][:, 0] & 0x7f == tape.OP_UNARY + it.I_componentwise).sum() == len(cw)
     assert len(tape.serialize(gen1, compiled=True)) > 0
+
+
+def test_allow_save_events_of_the_reference_driver():
+    """allowSave (cmex2optimizeCS.m:267,327; declareSave of ipmPD_CStimesLambda.m:288-290): the reference's unmodified
+    driver calls saveWW__ at iter == saveIter and, for saveIter == 0, at a successful exit
+    (ipmPD_CSsolver.c:561-566,671-676,877-882).  Here saveWW__ copies the KKT values into save variables that
+    getOutputs returns last: the solve itself is unchanged, the saved matrix is symmetric with the KKT dimension,
+    differs from one iteration to the next, and stays untouched when no event fires"""
+    from oracle.oracle import Oracle
+    from tenscalc_b200 import problems
+    gen0, args = generated("mpc_dcmotor")
+    gen, _ = generated("mpc_dcmotor", allowSave=True)
+    assert gen.defines["allowSave"] == 1 and "saveWW__" in gen.problem.copies and gen.outputs[-1][0] == "WW_values__"
+    subs = gen.info["WW_subscripts"]
+    n = gen.defines["nU"] + gen.defines["nG"] + gen.defines["nF"]
+    assert subs.shape == (gen.outputs[-1][1][0], 2) and subs.max() == n - 1
+    assert np.array_equal(subs, subs[np.lexsort((subs[:, 0], subs[:, 1]))])         # column-major order
+    P, V = problems.synthetic_inputs("mpc_dcmotor", gen0, 8, seed=1)
+    st0, it0, out0, _ = Oracle(gen0, "ref").solve_batch(P, V, args["mu0"], args["maxIter"])
+    o = Oracle(gen, "ref")
+    saved = {}
+    for si in (-1, 0, 3, 4):
+        st, it_, out, _ = o.solve_batch(P, V, args["mu0"], args["maxIter"], saveIter=si)
+        assert np.array_equal(st, st0) and np.array_equal(it_, it0)
+        for k in out0:
+            assert np.array_equal(out[k], out0[k]), k
+        saved[si] = out["WW_values__"]
+    assert (st0 == 0).all() and it0.min() > 4
+    assert not saved[-1].any()                                   # no event: the save variables were never written
+    for si in (0, 3, 4):
+        for b in range(8):
+            M = np.zeros((n, n))
+            M[subs[:, 0], subs[:, 1]] = saved[si][:, b]
+            assert np.array_equal(M, M.T) and np.abs(M).sum() > 0
+    assert np.abs(saved[3] - saved[4]).max() > 0 and np.abs(saved[0] - saved[4]).max() > 0
+    with pytest.raises(NotImplementedError, match="kind='ref'"):
+        Oracle(gen, "port").build()
