@@ -126,6 +126,11 @@ def save_scalarized(gen, filename: str, extended: bool = True, int_width: int = 
         elif t in (it.I_sum, it.I_sumprod):              # :166-172
             var = constant_variable(np.asarray(p, dtype=np.int64).reshape(-1, 1), "sum")
             w.ints("cg", [SCALAR_CODES[t], 1 + len(ops), 1, var, *ops, i])
+        elif t == it.I_componentwise:                    # private extension: the C text travels as a parameter vector
+            if not extended:                             # (saveScalarized has no code for it, :138-195)
+                raise CGFormatError(f"csparse/saveScalarized: missing type {t} ({it.OPNAMES.get(t)})")
+            var = constant_variable(np.asarray(p, dtype=np.int64).reshape(-1, 1), "componentwise")
+            w.ints("cg", [EXT_BASE + t, 1 + len(ops), 1, var, *ops, i])
         else:
             code = SCALAR_CODES.get(t)
             if code is None:
@@ -311,7 +316,7 @@ def load_scalarized(filename: str, classname: Optional[str] = None, output_shape
     # auxiliary variables (parameter vectors, subscripts, full tensors) are numbered after the table
     aux = [n[2][0] for n in nodes if n[0] == CG_CONST_FUNCTION and not _is_load(constants[n[1][0]])]
     aux += [n[2][0] for n in nodes if n[0] == CG_S2FT] + [n[1][0] for n in nodes if n[0] == CG_FT2S]
-    used = [v for n in nodes if n[0] not in (CG_CONST_FUNCTION, CG_S2FT, CG_FT2S) for v in n[1][(1 if n[0] in (20001, 20002) else 0):] + n[2]]
+    used = [v for n in nodes if n[0] not in (CG_CONST_FUNCTION, CG_S2FT, CG_FT2S) for v in n[1][(1 if n[0] in (20001, 20002, EXT_BASE + it.I_componentwise) else 0):] + n[2]]
     used += [n[2][0] for n in nodes if n[0] == CG_CONST_FUNCTION and _is_load(constants[n[1][0]])]
     used += [v for n in nodes if n[0] == CG_S2FT for v in n[1][1:]] + [v for n in nodes if n[0] == CG_FT2S for v in n[2]]
     used += [v for k, a, b in ios if k == CG_IO_COPY for v in a + b]
@@ -333,7 +338,7 @@ def load_scalarized(filename: str, classname: Optional[str] = None, output_shape
         if op is None or op not in it.OPNAMES:
             raise CGFormatError(f"unregistered function type {t} for variable {v}")
         params: Tuple[float, ...] = ()
-        if op in (it.I_sum, it.I_sumprod):
+        if op in (it.I_sum, it.I_sumprod, it.I_componentwise):
             pnode = produced.get(ins[0])
             if pnode is None or pnode[0] != CG_CONST_FUNCTION:
                 raise CGFormatError(f"variable {v}: parameter input {ins[0]} is not a constant")

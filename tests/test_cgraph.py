@@ -127,3 +127,22 @@ def test_loaded_problem_on_the_gpu(tmp_path):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
+
+
+def test_componentwise_text_survives_the_files(tmp_path):
+    """I_componentwise has no registered code in saveScalarized.m (:138-195): the extended writer stores the C text as
+    a parameter vector (like the sign vector of a sum) under a private type code, the reader restores it -- same
+    instruction table, same fingerprint, hence the same compiled module; the strict writer refuses"""
+    from tenscalc_b200 import itable as it
+    gen, _ = generated("isa_probe", cw=True)
+    base = str(tmp_path / "cw")
+    cgraph.save_scalarized(gen, base)
+    g2 = cgraph.load_scalarized(base, output_shapes={"getOutputs": [s for _, s in gen.outputs]})
+    pr, p2 = gen.problem, g2.problem
+    assert p2.tab.types == pr.tab.types and p2.tab.operands == pr.tab.operands and p2.tab.params == pr.tab.params
+    texts = sorted(it.componentwise_text(p2.tab.params[i], "%s") for i in range(len(p2.tab))
+                   if p2.tab.types[i] == it.I_componentwise)
+    assert texts == ["cos(%s)", "sin(%s)"]
+    assert fingerprint(p2) == fingerprint(pr)
+    with pytest.raises(cgraph.CGFormatError):
+        cgraph.save_scalarized(gen, str(tmp_path / "strict"), extended=False)
