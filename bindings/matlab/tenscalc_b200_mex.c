@@ -44,7 +44,14 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         *(uint64_t *)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)s;
     } else if (!strcmp(cmd, "set")) {
         tc_solver *s = handle(prhs[1]);
-        int idx = (int)mxGetScalar(prhs[2]);
+        int idx;
+        if (mxIsChar(prhs[2])) { /* by name, like the reference's <class>_set_<name> (writeCfunctionpergroup.m:524) */
+            char name[256];
+            if (mxGetString(prhs[2], name, sizeof name)) mexErrMsgTxt("set: bad name");
+            idx = tc_find_set(s, name);
+            if (idx < 0) mexErrMsgTxt("set: the class has no parameter or variable of that name");
+        } else
+            idx = (int)mxGetScalar(prhs[2]);
         int64_t n = tc_set_size(s, idx), total = (int64_t)mxGetNumberOfElements(prhs[3]);
         if (total != n && total != n * tc_batch(s)) mexErrMsgTxt("set: value must have n or n*batch entries");
         check(tc_set(s, idx, mxGetPr(prhs[3]), total == n ? 0 : n));

@@ -63,6 +63,14 @@ int tc_num_outputs(const tc_solver *s);
 int64_t tc_set_size(const tc_solver *s, int set_index);
 int64_t tc_output_size(const tc_solver *s, int output_index);
 int64_t tc_scratch_bytes(const tc_solver *s);
+/* Name lookup.  The reference exports one symbol per parameter / optimisation variable, `<class>_set_<name>`
+ * (lib/@csparse/writeCfunctionpergroup.m:524), and names its outputs (struct fields or y1, y2, ...:
+ * lib/cmex2optimizeCS.m:337-355); here a set function or an output is an index, and these map <name> to it.
+ * tc_find_*: index >= 0, or TC_EINVAL when the class has no such name; tc_*_name: NULL for a bad index. */
+int tc_find_set(const tc_solver *s, const char *name);
+int tc_find_output(const tc_solver *s, const char *name);
+const char *tc_set_name(const tc_solver *s, int set_index);
+const char *tc_output_name(const tc_solver *s, int output_index);
 
 /* <class>_set_<name>: `values` is double[batch][n] on the host (tc_set) or on the device
  * (tc_set_device).  With batch_stride==0 the same n values are broadcast to all instances. */

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../include/tenscalc_b200.h"
@@ -216,6 +217,7 @@ struct tc_solver {
     std::vector<void *> allocs;
     std::vector<tc_func> funcs;          // host copy
     std::vector<uint32_t> set_fids, out_sizes, out_offs;
+    std::vector<std::string> set_names, out_names;   // <name> of <class>_set_<name> / of the outputs (may be empty)
     int32_t *d_status = nullptr, *d_iter = nullptr;
     unsigned long long *d_sum = nullptr;
     double *d_stage = nullptr;           // staging for host<->device I/O
@@ -308,7 +310,23 @@ int tc_create(tc_solver **out, const void *image, size_t image_bytes, int64_t ba
     const uint32_t *set_fids = (const uint32_t *)p;    p += pad16(n_sets * 4);
     const uint32_t *out_sizes = (const uint32_t *)p;   p += pad16(n_out * 4);
     const uint32_t *persist = (const uint32_t *)p;     p += pad16(n_persist * 4);
+    const int64_t names_bytes = ih[13];                // 0: an image without names (tc_find_* then return TC_EINVAL)
+    const char *names = p;
+    if (names_bytes < 0 || (uint64_t)names_bytes > image_bytes) { delete s; return TC_EFORMAT; }
+    p += pad16((size_t)names_bytes);
     bool ok = (size_t)(p - (const char *)image) <= image_bytes;
+    if (ok && names_bytes > 0) {                       // n_sets + n_out NUL-terminated, non-empty names
+        int64_t k = 0;
+        for (const char *q = names; ok && q < names + names_bytes; k++) {
+            const void *z = memchr(q, 0, (size_t)(names + names_bytes - q));
+            ok = z != nullptr && z != q && k < n_sets + n_out;
+            if (ok) {
+                (k < n_sets ? s->set_names : s->out_names).emplace_back(q);
+                q = (const char *)z + 1;
+            }
+        }
+        ok = ok && k == n_sets + n_out;
+    }
     for (int64_t g = 0; ok && g < n_groups; g++) ok = group_start[g] <= group_start[g + 1] && group_start[g + 1] <= tape_cells;
     for (int64_t f = 0; ok && f < n_funcs; f++)
         ok = (uint64_t)funcs[f].io_off + funcs[f].io_cnt <= (uint64_t)io_words;
@@ -521,6 +539,21 @@ int tc_has_module(const tc_solver *s) { return s ? (s->module != nullptr) : TC_E
 
 int64_t tc_batch(const tc_solver *s) { return s ? s->batch : TC_EINVAL; }
 int tc_num_sets(const tc_solver *s) { return s ? (int)s->set_fids.size() : TC_EINVAL; }
+
+static int tc_find_name(const std::vector<std::string> &v, const char *name) {
+    for (size_t k = 0; k < v.size(); k++)
+        if (v[k] == name) return (int)k;
+    return TC_EINVAL;
+}
+// index of <class>_set_<name> / of output <name>; TC_EINVAL (negative) when there is no such name
+int tc_find_set(const tc_solver *s, const char *name) { return (s && name) ? tc_find_name(s->set_names, name) : TC_EINVAL; }
+int tc_find_output(const tc_solver *s, const char *name) { return (s && name) ? tc_find_name(s->out_names, name) : TC_EINVAL; }
+const char *tc_set_name(const tc_solver *s, int i) {
+    return (s && i >= 0 && (size_t)i < s->set_names.size()) ? s->set_names[i].c_str() : nullptr;
+}
+const char *tc_output_name(const tc_solver *s, int i) {
+    return (s && i >= 0 && (size_t)i < s->out_names.size()) ? s->out_names[i].c_str() : nullptr;
+}
 int tc_num_outputs(const tc_solver *s) { return s ? (int)s->out_sizes.size() : TC_EINVAL; }
 int64_t tc_set_size(const tc_solver *s, int i) {
     if (!s || i < 0 || i >= (int)s->set_fids.size()) return TC_EINVAL;

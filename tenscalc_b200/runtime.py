@@ -38,6 +38,10 @@ ABI = [
     ("tc_set_size", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
     ("tc_output_size", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
     ("tc_scratch_bytes", ctypes.c_int64, [ctypes.c_void_p]),
+    ("tc_find_set", ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    ("tc_find_output", ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    ("tc_set_name", ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
+    ("tc_output_name", ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
     ("tc_set", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
     ("tc_set_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
     ("tc_solve", ctypes.c_int, [ctypes.c_void_p, _dp, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p, _dp]),
@@ -167,11 +171,16 @@ class BatchedSolver:
                 lib.tc_destroy(h)
                 self._h = None
                 raise
+        # set functions by name, as the reference's `<class>_set_<name>` symbols: the handle resolves them
         self._set_index: Dict[str, int] = {}
-        for k, (n, _) in enumerate(gen.parameters):
-            self._set_index["P_" + n] = k
-        for k, (n, _) in enumerate(gen.variables):
-            self._set_index["V_" + n] = len(gen.parameters) + k
+        for kind, items in (("P_", gen.parameters), ("V_", gen.variables)):
+            for n, _ in items:
+                k = lib.tc_find_set(h, n.encode())
+                if k < 0:
+                    lib.tc_destroy(h)
+                    self._h = None
+                    raise TenscalcError(f"the problem image has no set function named {n}")
+                self._set_index[kind + n] = k
         self._shapes = {("P_" + n): s for n, s in gen.parameters}
         self._shapes.update({("V_" + n): s for n, s in gen.variables})
 

@@ -437,7 +437,16 @@ def serialize(gen: GeneratedSolver, compiled: bool = False) -> bytes:
     def pad16(b: bytes) -> bytes:
         return b + b"\0" * (-len(b) % 16)
 
+    # names of the set functions (the <name> of the reference's `<class>_set_<name>` symbols, parameters first, then
+    # optimisation variables: writeCfunctionpergroup.m:524) and of the outputs, NUL-terminated, in index order --
+    # what tc_find_set / tc_find_output look up
+    names = [n for n, _ in gen.parameters] + [n for n, _ in gen.variables] + [n for n, _ in gen.outputs]
+    blob = b"".join(n.encode() + b"\0" for n in names)
+    if len(names) != len(L["set_fids"]) + len(L["out_sizes"]) or any(not n or "\0" in n for n in names):
+        raise ValueError("set/output names do not match the set functions and outputs of the problem")
+    ih[13] = len(blob)
     parts = [ih.tobytes(), dh.tobytes()]
     for key in ("group_start", "tape", "consts", "funcs", "io", "set_fids", "out_sizes", "persist"):
         parts.append(pad16(np.ascontiguousarray(L[key]).tobytes()))
+    parts.append(pad16(blob))
     return b"".join(parts)

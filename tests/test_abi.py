@@ -92,3 +92,36 @@ def test_image_layout_roundtrip():
     assert (ih[16], ih[17], ih[18]) == (89, 60, 174)
     assert ih[1] == gen.problem.n_slots and ih[2] == len(gen.problem.groups)
     assert dh[0] == 1e-4 and dh[3] == 1e-5 and dh[4] == 1e-7 and dh[5] == 1.0
+    # the image ends with the names of the set functions and outputs (tc_find_set / tc_find_output), NUL-terminated
+    names = [n for n, _ in gen.parameters] + [n for n, _ in gen.variables] + [n for n, _ in gen.outputs]
+    blob = b"".join(n.encode() + b"\0" for n in names)
+    assert ih[13] == len(blob) and ih[30] == 0                      # allowSave off
+    assert img.rstrip(b"\0").endswith(blob.rstrip(b"\0"))
+    assert tape.serialize(generated("mpc_dcmotor", allowSave=True)[0])[30 * 8] == 1
+
+
+@pytest.mark.gpu
+def test_name_lookup(lib):
+    """`<class>_set_<name>` of the reference (writeCfunctionpergroup.m:524) is tc_set(h, tc_find_set(h, "<name>"), ...)
+    here: every parameter, variable and output of the class resolves to its index, unknown names do not, and a
+    truncated names section is a format error"""
+    from tenscalc_b200 import tape
+    gen, _ = generated("mpc_dcmotor")
+    img = tape.serialize(gen)
+    h = ctypes.c_void_p()
+    assert lib.tc_create(ctypes.byref(h), img, len(img), 64, 0) == 0
+    sets = [n for n, _ in gen.parameters] + [n for n, _ in gen.variables]
+    assert lib.tc_num_sets(h) == len(sets) and lib.tc_num_outputs(h) == len(gen.outputs)
+    for k, n in enumerate(sets):
+        assert lib.tc_find_set(h, n.encode()) == k and lib.tc_set_name(h, k) == n.encode()
+        shape = dict(gen.parameters + gen.variables)[n]
+        assert lib.tc_set_size(h, k) == (int(np.prod(shape)) if shape else 1)
+    for k, (n, _) in enumerate(gen.outputs):
+        assert lib.tc_find_output(h, n.encode()) == k and lib.tc_output_name(h, k) == n.encode()
+    assert lib.tc_find_set(h, b"no_such_parameter") == -1 and lib.tc_find_output(h, b"") == -1
+    assert lib.tc_set_name(h, len(sets)) is None and lib.tc_find_set(h, None) == -1
+    assert lib.tc_destroy(h) == 0
+    ih = np.frombuffer(img[:64 * 8], dtype=np.int64).copy()
+    ih[13] -= 3                                                     # the last name loses its terminator
+    bad = ih.tobytes() + img[64 * 8:]
+    assert lib.tc_create(ctypes.byref(h), bad, len(bad), 64, 0) == -2
