@@ -234,7 +234,9 @@ def run_reference(args, rank):
     gen, sargs = problems.BUILDERS[name](**(dict(ordering=args.ordering) if args.ordering else {}))
     so, kind = _oracle_library(gen)
     cores = host_cores()
-    per_core = args.cpu_sample or dict(mpc_quadcopter=24, l1l2=96, mpc_dcmotor=2048, sls=8192)[name]
+    # about half a second of work per core and step: long enough that the step's wall time (= the slowest core's) is
+    # not dominated by one unlucky slice of stragglers, short enough for --steps 20 --warmup 5 to end within a minute
+    per_core = args.cpu_sample or dict(mpc_quadcopter=192, l1l2=320, mpc_dcmotor=4096, sls=8192)[name]
     n = cores * per_core
     Pp, Vp, nY = _cpu_inputs(name, gen, n, seed=12345)
     pool = CpuPool(so, cores)
@@ -499,7 +501,7 @@ def run_ours(args, rank, local_rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:      # before CUDA is touched by this process
-        per_core = args.cpu_sample or dict(mpc_quadcopter=48, l1l2=256, mpc_dcmotor=8192, sls=32768)[name]
+        per_core = args.cpu_sample or dict(mpc_quadcopter=384, l1l2=640, mpc_dcmotor=8192, sls=32768)[name]   # ~1 s per core
         cpu = cpu_baseline(name, gen, sargs, per_core)
 
     torch.cuda.set_device(local_rank)
