@@ -25,7 +25,8 @@ classdef tenscalc_b200_solver < handle
         function setP(obj,name,value); obj.set(['P_',name],value); end
         function setV(obj,name,value); obj.set(['V_',name],value); end
         function set(obj,key,value)
-            k=find(strcmp(obj.names.sets,key))-1;
+            % by name: the image carries the <name> of the reference's <class>_set_<name> symbols (tc_find_set)
+            k=key(3:end);
             tenscalc_b200_mex('set',obj.h,k,reshape(double(value),[],size(value,ndims(value))*(numel(value)>1)+(numel(value)==1)));
         end
         function [status,iter,time]=solve(obj,mu0,maxIter,saveIter,addEye2Hessian)
