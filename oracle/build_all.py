@@ -8,7 +8,7 @@ from concurrent.futures import ProcessPoolExecutor
 AFFINE = {"algorithm": "ipmPD_CS", "skipAffine": False}           # Mehrotra predictor (ipmPD_CSsolver.c:576-665, ipmPD_CS.m)
 AFFINE_SMALL = {**AFFINE, "smallerNewtonMatrix": True}            # + reduced Newton matrix (ipmPD_CS.m:242-351)
 CONFIGS = [("sls", {}), ("mpc_dcmotor", {}), ("l1l2", {}), ("mpc_quadcopter", {}), ("isa_probe", {}),
-           ("mpc_dcmotor", {"allowSave": True}),                   # saveWW__ events of the reference driver (kind "ref" only)
+           ("mpc_dcmotor", {"allowSave": True}),                   # saveWW__ events of the drivers (ipmPD_CSsolver.c:330-332,561-566,...)
            ("isa_probe", {"cw": True}),                            # user-defined componentwise function (I_componentwise)
            ("mpc_quadcopter", {"T_": 20, "useInertia": True}),    # inertia-controlled regularisation (ipmPD_CSsolver.c:408-519)
            ("sls", AFFINE), ("mpc_dcmotor", AFFINE), ("mpc_dcmotor", AFFINE_SMALL),
@@ -50,7 +50,7 @@ def build_all(kinds=("ref", "port"), configs=CONFIGS, workers=4, extra=True):
     for N, n, lo, hi in DENSE:
         for k in kinds:
             print("oracle dense_ls", N, n, k, DenseOracle(N, n, lo, hi, k).build())
-    jobs = [(n, kw, k, "-O1", "") for n, kw in configs for k in kinds if k == "ref" or not kw.get("allowSave")]
+    jobs = [(n, kw, k, "-O1", "") for n, kw in configs for k in kinds]
     if "ref" in kinds:
         jobs += [(n, kw, "ref", "-O1", "") for n, kw in EQ_CONFIGS + MM_CONFIGS]
     if extra:

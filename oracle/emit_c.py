@@ -225,10 +225,8 @@ def emit_translation_unit(gen: GeneratedSolver, emitter: str = "port", driver: s
     if int(pr.defines.get("allowSave", 0)):
         # allowSave: the reference's driver calls saveWW__(saveNamePrefix "_WW.values") (ipmPD_CSsolver.c:51,330-332,
         # 561-566,671-676,699-703,877-882).  The oracle's saveWW__ is the copy of the KKT values into the save
-        # variables that getOutputs returns (optimize.py), the file name is ignored (the driver still prints its
-        # "Saving ..." line per event).  Only the reference's own driver carries the save hooks.
-        if driver != "ref":
-            raise NotImplementedError("allowSave: use the reference's driver as oracle (kind='ref')")
+        # variables that getOutputs returns (optimize.py), the file name is ignored (the reference's driver
+        # still prints its "Saving ..." line per event; the port driver has the same hooks, without the print).
         w('#define saveNamePrefix "oracle"\n')
     for c in pr.copies.values():
         sig = "char *filename" if c.name == "saveWW__" else "void"

@@ -66,6 +66,14 @@ static double p_line_search(double aMax) {
 }
 #endif
 
+/* allowSave: the reference dumps the KKT values with saveWW__(file) at these events (:330-332,561-566,671-676,
+ * 699-703,877-882); the generated saveWW__ of the oracle copies them into the save variables getOutputs returns */
+#if allowSave != 0
+#define P_SAVE_WW() saveWW__("")
+#else
+#define P_SAVE_WW() ((void)0)
+#endif
+
 EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, double *addEye2Hessian,
                            int32_t *status, int32_t *iter, double *time) {
     (void)saveIter;
@@ -108,7 +116,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
         if (++*iter > *maxIter) { *status = 8; break; }          /* :284,308-313 */
 
         getNorminf_Grad__(&grad);                                /* :323-335 */
-        if (isnan(grad)) { *status = 4; break; }
+        if (isnan(grad)) { *status = 4; P_SAVE_WW(); break; }   /* :326-334 */
 #if nG > 0
         getNorminf_G__(&eq);                                     /* :337-339 */
 #endif
@@ -177,6 +185,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
 #if nG > 0
         setAlphaDualEq__(&aMax);
 #endif
+        if (*iter == *saveIter) P_SAVE_WW();                     /* :561-566 */
         updatePrimalDual__();
 #else
 #if skipAffine == 0
@@ -223,6 +232,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
             }
         }
 #endif
+        if (*iter == *saveIter) P_SAVE_WW();                     /* :671-676 */
         getMaxAlphas_s__(&aP, &aDi);                             /* :679 */
 #if coupledAlphas != 0
         if (aDi < aP) aP = aDi;                                  /* :681-684 */
@@ -230,7 +240,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
         aP *= P_STEPBACK;
         aMax = (aP < alphaMax) ? aP : alphaMax;                  /* :688 */
         aP = p_line_search(aMax);
-        if (isnan(aP)) { *status = 4; break; }
+        if (isnan(aP)) { *status = 4; P_SAVE_WW(); break; }      /* :696-704 */
 #if coupledAlphas != 0
         aDe = aP;                                                /* :758-767 */
         aDi = aP;
@@ -276,6 +286,7 @@ EXPORT void ipmPD_CSsolver(double *mu0, int32_t *maxIter, int32_t *saveIter, dou
 #endif
     }
 
+    if (*saveIter == 0 && *status == 0) P_SAVE_WW();             /* :877-882 */
     if (*status == 8) {                                          /* :885-920 */
         getNorminf_Grad__(&grad);
         if (grad > gradTolerance) *status |= 16;

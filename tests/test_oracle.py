@@ -365,5 +365,8 @@ def test_allow_save_events_of_the_reference_driver():
             M[subs[:, 0], subs[:, 1]] = saved[si][:, b]
             assert np.array_equal(M, M.T) and np.abs(M).sum() > 0
     assert np.abs(saved[3] - saved[4]).max() > 0 and np.abs(saved[0] - saved[4]).max() > 0
-    with pytest.raises(NotImplementedError, match="kind='ref'"):
-        Oracle(gen, "port").build()
+    # the port driver carries the same hooks: bit-identical kept values
+    for si in (0, 3):
+        st, it_, out, _ = Oracle(gen, "port").solve_batch(P, V, args["mu0"], args["maxIter"], saveIter=si)
+        assert np.array_equal(st, st0) and np.array_equal(it_, it0)
+        assert np.array_equal(out["WW_values__"], saved[si])
